@@ -1,0 +1,193 @@
+/*
+ * vae_b200.h -- C ABI of the B200-native VAE ELBO train-step library (libvae_b200.so).
+ *
+ * The reference (virajmehta/vae-training) has no FFI / plugin interface: it is pure
+ * Python on JAX/Flax.  The drop-in boundary is therefore the set of Python call
+ * seams listed in SURVEY.md 8(b); each entry point below names the reference
+ * call site it replaces (paths are into the reference tree).  A jax.ffi handler
+ * would bind exactly these symbols.
+ *
+ * Conventions
+ *   - Every pointer documented "device" is a CUDA device pointer owned by the
+ *     caller, 16-byte aligned.  The callee never allocates, frees or retains a
+ *     pointer past return.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL is the
+ *     legacy default stream).  No entry point synchronises the device.
+ *   - Return value: 0 on success, negative VAE_ERR_* otherwise; the message is
+ *     available from vae_last_error() (thread-local).
+ *   - No global mutable state: re-entrant across host threads / streams / devices.
+ *   - There is no CPU fallback anywhere behind this header.
+ *
+ * Tensors are float32 row-major; PRNG keys are uint32[2] (jax.random legacy
+ * threefry2x32 layout).
+ */
+#ifndef VAE_B200_H_
+#define VAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAE_B200_ABI_VERSION 1
+#define VAE_MAX_HIDDEN 8
+
+enum {
+  VAE_OK = 0,
+  VAE_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  VAE_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  VAE_ERR_WORKSPACE = -3, /* workspace too small */
+  VAE_ERR_UNSUPPORTED = -4
+};
+
+/* Model description.  Mirrors the keyword arguments VAE.partial(...) is given at
+ * vae.py:57-59 plus the optimiser hyper-parameters of vae.py:113 and the batch
+ * size of run.py:14. */
+typedef struct VaeDesc {
+  int32_t batch;                      /* B          run.py:14                       */
+  int32_t data_dim;                   /* D          vae.py:51 (prod(dataset.shape)) */
+  int32_t latent_dim;                 /* L          run.py:22                       */
+  int32_t n_enc_hidden;               /* len(encoder_layer_sizes) - 1   vae.py:53   */
+  int32_t enc_hidden[VAE_MAX_HIDDEN];
+  int32_t n_dec_hidden;               /* len(decoder_layer_sizes) - 1   vae.py:54   */
+  int32_t dec_hidden[VAE_MAX_HIDDEN];
+  int32_t sig_decoder;                /* dataset_name == "sigmoid"  networks.py:75  */
+  int32_t tunable_decoder_var;        /* -tdv                       networks.py:70  */
+  float epsilon0;                     /* --epsilon                  run.py:32       */
+  float lr;                           /* -lr                        run.py:15       */
+  float beta1, beta2, adam_eps;       /* flax.optim.Adam defaults .9 .999 1e-8      */
+} VaeDesc;
+
+/* Flat parameter layout (params, adam_m, adam_v and gradients all use it):
+ *   for net in Encoder, Decoder, [SigDecoder if sig_decoder]:
+ *     for layer i: kernel (in, out) row-major, then bias (out)
+ *   epsilon_p (L)                    networks.py:69
+ *   epsilon   (1) if tunable_decoder_var   networks.py:71
+ */
+int64_t vae_param_count(const VaeDesc* desc);
+
+/* Synthetic generator description (run.py:46-54, datasets.py:55-98,163-228,230-279). */
+enum { VAE_DATA_SPHERE = 0, VAE_DATA_LINEAR_GAUSSIAN = 1, VAE_DATA_SIGMOID = 2 };
+typedef struct VaeDataDesc {
+  int32_t kind;            /* VAE_DATA_*                                          */
+  int32_t dim;             /* -dd  dataset_dimension                              */
+  int32_t padding_dim;     /* --padding_dim                                       */
+  int32_t intrinsic_dim;   /* -did (linear_gaussian only; run.py:37 default 3)    */
+} VaeDataDesc;
+/* Row width of a generated batch: dim+padding (+1 for sigmoid, datasets.py:235). */
+int32_t vae_data_width(const VaeDataDesc* d);
+/* Normals consumed per generated row: dim (sphere, sigmoid) / intrinsic_dim (linear). */
+int32_t vae_data_normals_per_row(const VaeDataDesc* d);
+
+/* ------------------------------------------------------------------ jax.random
+ * Replaces random.split (vae.py:56,125; model.py:140,154,208; datasets.py:51).
+ * d_key: device uint32[2]; d_out: device uint32[num*2]. */
+int vae_random_split(const uint32_t* d_key, uint32_t* d_out, int32_t num, void* stream);
+/* Raw threefry2x32 bits over iota(n) (jax._random_bits). */
+int vae_random_bits(const uint32_t* d_key, uint32_t* d_out, int64_t n, void* stream);
+/* Replaces random.normal(key, shape) float32 (model.py:227; datasets.py:76,173,185,237,242).
+ * Bits are exact; floats are bit-identical to oracle/jax_random.py. */
+int vae_random_normal(const uint32_t* d_key, float* d_out, int64_t n, void* stream);
+/* Rows [row_begin, row_end) of the (rows, cols) array random.normal(key, (rows, cols))
+ * would return, written densely to d_out ((row_end-row_begin) x cols).  Used by the
+ * data-parallel path so every rank draws exactly its own slice of eps. */
+int vae_random_normal_rows(const uint32_t* d_key, float* d_out, int64_t rows, int64_t cols,
+                           int64_t row_begin, int64_t row_end, void* stream);
+
+/* -------------------------------------------------------------------- datasets
+ * Replaces <Dataset>.get_batch(size) given the already-split batch key
+ * (datasets.py:75-84, 183-195, 240-249).  d_A: device generator matrix
+ * (dim x intrinsic_dim for linear, dim x 1 for sigmoid, ignored for sphere).
+ * d_out: device (size, vae_data_width) float32. */
+int vae_dataset_batch(const VaeDataDesc* d, const uint32_t* d_key, const float* d_A,
+                      int32_t size, float* d_out, void* stream);
+/* Replaces <Dataset>.score_batch(batch) (datasets.py:67-73, 201-206, 255-261).
+ * d_scores: device float[2] = {first, second} statistic in the reference's dict order
+ * (second is 0 for linear_gaussian). */
+int vae_dataset_score(const VaeDataDesc* d, const float* d_A, const float* d_batch,
+                      int32_t size, float* d_scores, void* stream);
+
+/* ------------------------------------------------------------------- VAE step
+ * Workspace the step / loss / sample entry points need, in bytes, for `rows` rows. */
+size_t vae_workspace_bytes(const VaeDesc* desc, int32_t rows);
+
+/* Replaces VAE.train_step(optimizer, batch, z1, z2, epsilon) (networks.py:87-101,
+ * called at vae.py:129).  params/adam_m/adam_v: device float[vae_param_count],
+ * updated in place; d_step: device int32 (number of updates applied so far,
+ * incremented); d_x: device (B, D); d_z: device (B, L+D) = [z1 | z2] exactly as
+ * model.py:227 draws it; d_loss: device float[1]. */
+int vae_train_step(const VaeDesc* desc, float* params, float* adam_m, float* adam_v,
+                   int32_t* d_step, const float* d_x, const float* d_z, float* d_loss,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient only (no update): d_grad device float[vae_param_count].  Used by the
+ * data-parallel path (allreduce between gradient and update) and by parity tests.
+ * grad_scale_rows: the B the mean at networks.py:98 divides by (global batch). */
+int vae_loss_and_grad(const VaeDesc* desc, const float* params, const float* d_x,
+                      const float* d_z, int32_t rows, int32_t grad_scale_rows,
+                      float* d_loss, float* d_grad, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* flax.optim.Adam.apply_gradient (networks.py:100) on a flat gradient. */
+int vae_adam_update(const VaeDesc* desc, float* params, float* adam_m, float* adam_v,
+                    int32_t* d_step, const float* d_grad, void* stream);
+
+/* Replaces VAE.loss(model, batch, z1, z2, epsilon) (networks.py:103-113, called at
+ * vae.py:135) on `rows` rows.  d_out: device float[3] = {loss, dkl.mean, mse.mean};
+ * logvar_e / epsilon are parameters the caller already holds. */
+int vae_loss(const VaeDesc* desc, const float* params, const float* d_x, const float* d_z,
+             int32_t rows, float* d_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the sampling-mode forward (networks.py:62-65 through vae.py:191-201).
+ * d_current_epsilon: device float[1] (self.current_epsilon); d_xhat: device (rows, D). */
+int vae_sample(const VaeDesc* desc, const float* params, const float* d_z, int32_t rows,
+               const float* d_current_epsilon, float* d_xhat, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------- fused training loop
+ * One job = one model of the sweep.  Replaces the body of the hot loop
+ * model.py:221-222 (dataset.get_batch + train_one_batch: key splits, eps draw,
+ * generator, forward, loss, backward, Adam) for n_steps consecutive steps, for
+ * every job, in ONE persistent launch.  Eval / plot events (model.py:214-220) are
+ * scheduled by the caller between launches.  All pointers are device pointers. */
+typedef struct VaeTrainJob {
+  VaeDesc desc;
+  VaeDataDesc data;
+  float* params;            /* [P] in/out */
+  float* adam_m;            /* [P] in/out */
+  float* adam_v;            /* [P] in/out */
+  int32_t* step;            /* [1] in/out */
+  uint32_t* model_key;      /* [2] in/out  carried model-side key (row 1 rule)   */
+  uint32_t* dataset_key;    /* [2] in/out  carried dataset-side key (row 0 rule) */
+  const float* A;           /* generator matrix or NULL                          */
+  float* loss_out;          /* [n_steps] out: per-step train loss                */
+  void* workspace;          /* vae_train_fused_workspace_bytes(job) bytes, or NULL if 0 */
+} VaeTrainJob;
+
+/* >0 if a fused persistent kernel exists for this job's shape (1 = single-CTA
+ * kernel, 2 = thread-block-cluster kernel), else 0. */
+int vae_train_fused_supported(const VaeTrainJob* job);
+size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job);
+/* Device scratch the launch needs for its job table. */
+size_t vae_train_fused_scratch_bytes(int32_t n_jobs);
+/* jobs: HOST array of n_jobs descriptors, all of the same vae_train_fused_supported()
+ * class.  d_scratch: device buffer of vae_train_fused_scratch_bytes(n_jobs) bytes
+ * (the job table is copied into it on `stream`; it must stay untouched until the
+ * launch has completed). */
+int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
+                    size_t scratch_bytes, void* stream);
+
+/* ----------------------------------------------------------------------- misc */
+const char* vae_last_error(void);
+int vae_abi_version(void);
+/* FP32 FFMA throughput probe (the roofline denominator for the small-model
+ * configs): runs `iters` dependent-chain FFMA batches on every SM; d_sink device
+ * float[>= blocks*threads]; *flops_out = total flops issued. */
+int vae_ffma_probe(float* d_sink, int32_t blocks, int32_t threads, int32_t iters,
+                   double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAE_B200_H_ */

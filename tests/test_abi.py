@@ -1,0 +1,87 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/vae_b200.h
+declares; host-only entry points (shape helpers, error reporting) behave.  No compute call
+is made here (no GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vae_training_b200 import _lib, build
+    build.build()                      # no-op when up to date; nvcc cross-compiles without a GPU
+    return _lib
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "vae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 20
+    handle = C.CDLL(lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"declared in include/vae_b200.h but not exported: {missing}"
+    assert sorted(lib.EXPORTED_SYMBOLS) == names, "ctypes prototypes out of sync with the header"
+
+
+def test_no_torch_types_or_cxx_mangling_in_abi(lib):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    ours = [s for s in exported if s.startswith("vae_")]
+    assert set(declared_functions()) <= set(ours)
+
+
+def test_struct_layout_matches_header(lib):
+    # VaeDesc: 3 + 1 + 8 + 1 + 8 + 2 int32, 5 floats
+    assert C.sizeof(lib.VaeDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 2 + 5)
+    assert C.sizeof(lib.VaeDataDesc) == 16
+    assert C.sizeof(lib.VaeTrainJob) == C.sizeof(lib.VaeDesc) + 16 + 9 * 8
+
+
+def test_host_side_helpers(lib):
+    L = lib.load()
+    assert L.vae_abi_version() == 1
+    d = lib.make_desc(100, 7, 6, sig_decoder=True)
+    assert L.vae_param_count(C.byref(d)) == 153
+    h = (200, 200, 200)
+    assert L.vae_param_count(C.byref(lib.make_desc(100, 21, 16, h, h))) == 176054
+    assert L.vae_param_count(C.byref(lib.make_desc(100, 12, 20, tunable_decoder_var=False))) == 532
+    assert L.vae_param_count(C.byref(lib.make_desc(100, 0, 6))) < 0
+    assert b"positive" in L.vae_last_error()
+    assert L.vae_data_width(C.byref(lib.make_data_desc("sigmoid", 3, 3))) == 7
+    assert L.vae_data_width(C.byref(lib.make_data_desc("sphere", 3, 13))) == 16
+    assert L.vae_data_normals_per_row(C.byref(lib.make_data_desc("linear_gaussian", 12, 8))) == 3
+    assert L.vae_workspace_bytes(C.byref(d), 100) > 0
+    assert L.vae_train_fused_scratch_bytes(54) >= 54 * 64
+
+
+def test_fused_supported_table(lib):
+    L = lib.load()
+
+    def job(name, dd, pd, lat, hidden=()):
+        j = lib.VaeTrainJob()
+        width = dd + pd + (1 if name == "sigmoid" else 0)
+        j.desc = lib.make_desc(100, width, lat, hidden, hidden, sig_decoder=(name == "sigmoid"))
+        j.data = lib.make_data_desc(name, dd, pd)
+        return j
+
+    assert L.vae_train_fused_supported(C.byref(job("linear_gaussian", 3, 9, 20))) == 1
+    assert L.vae_train_fused_supported(C.byref(job("sigmoid", 7, 20, 24))) == 1
+    assert L.vae_train_fused_supported(C.byref(job("sigmoid", 7, 20, 23))) == 0
+    assert L.vae_train_fused_supported(C.byref(job("sphere", 3, 3, 6, (200, 200, 200)))) in (0, 2)
+
+
+def test_missing_library_fails_loudly(lib, monkeypatch):
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libvae_b200.so")
+    with pytest.raises(lib.VaeB200Error):
+        lib.load()

@@ -1,0 +1,382 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (vae_training_b200.ops ->
+libvae_b200.so), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * integer work (threefry bits, key splits, key chains): bit-exact;
+  * sampled eps and dataset draws: bit-exact with oracle/jax_random.py, oracle/datasets.py;
+  * per-step loss / gradients / parameters: float32 tolerance, rel 1e-5 per step
+    (checked against the oracle's float64 shadow where the oracle's own float32
+    rounding would otherwise dominate).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import datasets as ods
+from oracle import jax_random as jr
+from oracle import trainer as otr
+from oracle import vae_step as vs
+
+pytestmark = pytest.mark.gpu
+
+REL_STEP = 1e-5          # north_star: rel 1e-5 per step
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vae_training_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vae_training_b200 import _lib
+    return _lib
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+# ------------------------------------------------------------------ jax.random
+
+@pytest.mark.parametrize("seed", [0, 42, 69, (7 << 32) | 5])
+def test_split_bit_exact(ops, seed):
+    key = jr.PRNGKey(seed)
+    for num in (2, 3, 7):
+        got = ops.random_split(ops.key_tensor(key), num).cpu().numpy()
+        np.testing.assert_array_equal(got, jr.split(key, num))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 1300, 1301, 5900, 65537, 1 << 20])
+def test_bits_and_normal_bit_exact(ops, n):
+    key = jr.PRNGKey(1234 + n)
+    k = ops.key_tensor(key)
+    np.testing.assert_array_equal(ops.random_bits(k, n).cpu().numpy(), jr.random_bits(key, n))
+    got = ops.random_normal(k, (n,)).cpu().numpy()
+    ref = jr.normal(key, (n,))
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_normal_empty_and_documented_values(ops):
+    assert ops.random_normal(ops.key_tensor(jr.PRNGKey(0)), (0,)).numel() == 0
+    assert float(ops.random_normal(ops.key_tensor(jr.PRNGKey(0)), ())) == np.float32(-0.20584226)
+    assert float(ops.random_normal(ops.key_tensor(jr.PRNGKey(42)), ())) == np.float32(-0.18471177)
+    # the eps draw of training step 0 of every run
+    z = ops.random_normal(ops.key_tensor(np.array([145021652, 2649282573], np.uint32)), (100, 13)).cpu().numpy()
+    np.testing.assert_allclose(z[0, :4], [1.2180066, 0.54291487, 0.52794409, 0.31873378], rtol=2e-7)
+
+
+def test_normal_large_covers_tail_branch(ops):
+    key = jr.PRNGKey(99)
+    n = 3_000_001
+    got = ops.random_normal(ops.key_tensor(key), (n,)).cpu().numpy()
+    ref = jr.normal(key, (n,))
+    assert (np.abs(ref) > 2.93).sum() > 5000
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("rows,cols,lo,hi", [(100, 13, 0, 100), (100, 13, 17, 63), (64, 33, 32, 64), (7, 3, 6, 7), (8, 5, 3, 3)])
+def test_normal_rows_matches_slice(ops, rows, cols, lo, hi):
+    key = jr.PRNGKey(5)
+    got = ops.random_normal_rows(ops.key_tensor(key), rows, cols, lo, hi).cpu().numpy()
+    ref = jr.normal(key, (rows, cols))[lo:hi]
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+# -------------------------------------------------------------------- datasets
+
+DATASETS = [("sphere", 3, 3), ("sphere", 7, 7), ("linear_gaussian", 3, 9), ("linear_gaussian", 12, 8),
+            ("sigmoid", 3, 3), ("sigmoid", 7, 20), ("sphere", 5, 0)]
+
+
+@pytest.mark.parametrize("name,dd,pd", DATASETS)
+@pytest.mark.parametrize("size", [100, 1000, 1])
+def test_dataset_batch_bit_exact(ops, lib, name, dd, pd, size):
+    ds = ods.make_dataset(name, 69, dd, pd)
+    key = ds.key.copy()
+    ref = ds.get_batch(size)
+    bkey, _ = jr.dataset_chain_next(key)
+    A = dev(ds.A.astype(np.float32)) if ds.A is not None else None
+    got = ops.dataset_batch(lib.make_data_desc(name, dd, pd), ops.key_tensor(bkey), A, size).cpu().numpy()
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,dd,pd", DATASETS[:6])
+def test_dataset_score(ops, lib, name, dd, pd):
+    ds = ods.make_dataset(name, 24, dd, pd)
+    rng = np.random.default_rng(0)
+    batch = (ds.get_batch(1000) + 0.1 * rng.standard_normal((1000, ds.ndim))).astype(np.float32)
+    ref = list(ds.score_batch(batch).values())
+    A = dev(ds.A.astype(np.float32)) if ds.A is not None else None
+    got = ops.dataset_score(lib.make_data_desc(name, dd, pd), A, dev(batch)).cpu().numpy()
+    for g, r in zip(got, ref):
+        assert abs(g - float(r)) <= 2e-5 * abs(float(r)) + 1e-7
+
+
+# -------------------------------------------------------------------- VAE step
+
+def odesc_to_c(lib, d: vs.VaeDesc):
+    return lib.make_desc(d.batch, d.data_dim, d.latent_dim, d.enc_hidden, d.dec_hidden, d.sig_decoder,
+                         d.tunable_decoder_var, d.epsilon0, d.lr, d.beta1, d.beta2, d.adam_eps)
+
+
+STEP_CASES = {
+    "linear_12_20": vs.VaeDesc(100, 12, 20, epsilon0=-1.0, lr=1e-3),
+    "sigmoid_7_6": vs.VaeDesc(100, 7, 6, sig_decoder=True, epsilon0=-3.0),
+    "sigmoid_28_24": vs.VaeDesc(100, 28, 24, sig_decoder=True, epsilon0=-3.0),
+    "sphere_6_6_h200": vs.VaeDesc(100, 6, 6, [200, 200, 200], [200, 200, 200], epsilon0=-3.0),
+    "sphere_21_16_h200": vs.VaeDesc(100, 21, 16, [200, 200, 200], [200, 200, 200], epsilon0=-3.0),
+    "fixed_var_ragged": vs.VaeDesc(37, 5, 3, [17], [9, 33], tunable_decoder_var=False, epsilon0=-0.5),
+    "wide_batch": vs.VaeDesc(1000, 16, 8, [64, 48], [48, 64], epsilon0=-2.0),
+}
+
+
+def make_inputs(d: vs.VaeDesc, seed=0, rows=None):
+    rng = np.random.default_rng(seed)
+    rows = rows or d.batch
+    flat = vs.init_params(d, seed=seed + 1)
+    flat = (flat + 0.02 * rng.standard_normal(flat.size)).astype(np.float32)
+    x = rng.standard_normal((rows, d.data_dim)).astype(np.float32)
+    z = rng.standard_normal((rows, d.latent_dim + d.data_dim)).astype(np.float32)
+    return flat, x, z
+
+
+@pytest.mark.parametrize("name", list(STEP_CASES))
+def test_loss_and_grad_vs_oracle(ops, lib, name):
+    d = STEP_CASES[name]
+    cd = odesc_to_c(lib, d)
+    assert ops.param_count(cd) == d.n_params
+    flat, x, z = make_inputs(d)
+    L = d.latent_dim
+    l64, g64 = vs.loss_and_grad(d, flat.astype(np.float64), x, z[:, :L], z[:, L:], dtype=np.float64)
+    l32, g32 = vs.loss_and_grad(d, flat, x, z[:, :L], z[:, L:])
+    loss = torch.zeros(1, device="cuda")
+    grad = torch.zeros(d.n_params, device="cuda")
+    ops.loss_and_grad(cd, dev(flat), dev(x), dev(z), d.batch, d.batch, loss, grad, ops.Workspace())
+    assert abs(float(loss) - l64) <= REL_STEP * abs(l64)
+    g = grad.cpu().numpy()
+    # as close to the float64 truth as the float32 oracle is (x4), and within 1e-5 of it
+    assert relerr(g, g64) <= max(4 * relerr(g32, g64), 2e-6)
+    assert relerr(g, g64) <= REL_STEP
+
+
+@pytest.mark.parametrize("name", list(STEP_CASES))
+def test_train_steps_vs_oracle(ops, lib, name):
+    """20 consecutive train_step calls (networks.py:87-101) on the same inputs as the oracle."""
+    d = STEP_CASES[name]
+    cd = odesc_to_c(lib, d)
+    flat, _, _ = make_inputs(d)
+    P = dev(flat)
+    M = torch.zeros_like(P)
+    V = torch.zeros_like(P)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    ws = ops.Workspace()
+    of, om, ov, ostep = flat.astype(np.float64), np.zeros(d.n_params), np.zeros(d.n_params), 0
+    L = d.latent_dim
+    for it in range(20):
+        _, x, z = make_inputs(d, seed=100 + it)
+        ops.train_step(cd, P, M, V, step, dev(x), dev(z), loss, ws)
+        of, om, ov, ostep, ol = vs.train_step(d, of, om, ov, ostep, x, z[:, :L], z[:, L:], dtype=np.float64)
+        assert abs(float(loss) - ol) <= REL_STEP * abs(ol), f"step {it}"
+    assert int(step) == 20
+    # Adam's first steps move every parameter by ~lr regardless of gradient size, so the
+    # comparison is absolute in units of lr: 20 steps, each within 1e-3 * lr
+    assert np.max(np.abs(P.cpu().numpy() - of)) <= 20 * 1e-3 * d.lr + 1e-7
+
+
+@pytest.mark.parametrize("name", ["sigmoid_7_6", "sphere_6_6_h200", "fixed_var_ragged"])
+def test_loss_and_sample_vs_oracle(ops, lib, name):
+    d = STEP_CASES[name]
+    cd = odesc_to_c(lib, d)
+    rows = 1000
+    flat, x, z = make_inputs(d, rows=rows)
+    L = d.latent_dim
+    ws = ops.Workspace()
+    got = ops.vae_loss(cd, dev(flat), dev(x), dev(z), rows, ws).cpu().numpy()
+    ref = vs.loss_terms(d, flat.astype(np.float64), x, z[:, :L], z[:, L:], dtype=np.float64)[:3]
+    for g, r in zip(got, ref):
+        assert abs(g - r) <= REL_STEP * abs(r)
+    cur = np.array([-2.5], np.float32)
+    xs = ops.vae_sample(cd, dev(flat), dev(z), rows, dev(cur), ws).cpu().numpy()
+    xr = vs.sample(d, flat.astype(np.float64), z[:, :L], z[:, L:], cur, dtype=np.float64)
+    assert relerr(xs, xr) <= REL_STEP
+
+
+def test_grad_scale_rows_shards_sum_to_full(ops, lib):
+    """Data-parallel contract: per-shard gradients scaled by the global batch add up to the
+    full-batch gradient."""
+    d = STEP_CASES["wide_batch"]
+    cd = odesc_to_c(lib, d)
+    flat, x, z = make_inputs(d)
+    ws = ops.Workspace()
+    full = torch.zeros(d.n_params, device="cuda")
+    lf = torch.zeros(1, device="cuda")
+    ops.loss_and_grad(cd, dev(flat), dev(x), dev(z), d.batch, d.batch, lf, full, ws)
+    acc = torch.zeros_like(full)
+    lacc = 0.0
+    for lo, hi in ((0, 250), (250, 1000)):
+        g = torch.zeros_like(full)
+        ls = torch.zeros(1, device="cuda")
+        ops.loss_and_grad(cd, dev(flat), dev(x[lo:hi]), dev(z[lo:hi]), hi - lo, d.batch, ls, g, ws)
+        acc += g
+        lacc += float(ls)
+    assert relerr(acc.cpu().numpy(), full.cpu().numpy()) <= 2e-6
+    assert abs(lacc - float(lf)) <= 2e-6 * abs(float(lf))
+
+
+# ---------------------------------------------------------------- error behaviour
+
+def test_errors_are_loud(ops, lib):
+    with pytest.raises(lib.VaeB200Error):
+        ops.random_normal(torch.zeros(2, dtype=torch.uint32), (4,))          # CPU tensor
+    bad = lib.make_desc(100, 0, 6)
+    with pytest.raises(lib.VaeB200Error):
+        ops.param_count(bad)
+    d = STEP_CASES["sigmoid_7_6"]
+    cd = odesc_to_c(lib, d)
+    flat, x, z = make_inputs(d)
+    import ctypes as C
+    rc = lib.load().vae_loss(C.byref(cd), C.c_void_p(dev(flat).data_ptr()), C.c_void_p(dev(x).data_ptr()),
+                             C.c_void_p(dev(z).data_ptr()), 100, C.c_void_p(torch.zeros(3, device="cuda").data_ptr()),
+                             C.c_void_p(0), 0, C.c_void_p(0))
+    assert rc == -3 and b"workspace" in lib.load().vae_last_error()
+
+
+# ------------------------------------------------------------- fused training loop
+
+FUSED_CASES = [
+    # (dataset, dd, pd, L, lr, eps0, seed)
+    ("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2),
+    ("linear_gaussian", 3, 17, 20, 1e-3, -1.0, 3),
+    ("linear_gaussian", 6, 6, 20, 1e-3, -1.0, 4),
+    ("linear_gaussian", 6, 14, 20, 1e-3, -1.0, 2),
+    ("linear_gaussian", 9, 3, 20, 1e-3, -1.0, 3),
+    ("linear_gaussian", 9, 11, 10, 1e-3, -1.0, 4),
+    ("linear_gaussian", 12, 8, 10, 1e-3, -1.0, 2),
+    ("sigmoid", 3, 3, 6, 1e-4, -3.0, 69),
+    ("sigmoid", 3, 13, 8, 1e-4, -3.0, 24),
+    ("sigmoid", 5, 16, 16, 1e-4, -3.0, 48),
+    ("sigmoid", 5, 5, 10, 1e-4, -3.0, 69),
+    ("sigmoid", 7, 7, 13, 1e-4, -3.0, 24),
+    ("sigmoid", 7, 20, 24, 1e-4, -3.0, 48),
+    ("sphere", 3, 3, 6, 1e-4, -3.0, 69),
+]
+
+
+def fused_setup(ops, lib, case, n_steps, batch=100, tunable=True):
+    name, dd, pd, L, lr, eps0, seed = case
+    ds = ods.make_dataset(name, seed, dd, pd)
+    D = ds.ndim
+    d = vs.VaeDesc(batch, D, L, sig_decoder=(name == "sigmoid"), epsilon0=eps0, lr=lr,
+                   tunable_decoder_var=tunable)
+    flat = vs.init_params(d, seed=0)
+    tr = otr.OracleTrainer(d, ds, flat, dtype=np.float64)
+    tr.begin()                                   # model.py:208-209
+    st = dict(
+        P=dev(flat), M=torch.zeros(d.n_params, device="cuda"), V=torch.zeros(d.n_params, device="cuda"),
+        step=torch.zeros(1, dtype=torch.int32, device="cuda"),
+        mk=ops.key_tensor(tr.key), dk=ops.key_tensor(ds.key),
+        A=dev(ds.A.astype(np.float32)) if ds.A is not None else None,
+        loss=torch.zeros(max(n_steps, 1), device="cuda"),
+    )
+    job = ops.make_job(odesc_to_c(lib, d), lib.make_data_desc(name, dd, pd), st["P"], st["M"], st["V"], st["step"],
+                       st["mk"], st["dk"], st["A"], st["loss"])
+    return d, ds, tr, st, job
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: f"{c[0]}_dd{c[1]}_pd{c[2]}_L{c[3]}")
+def test_fused_small_vs_oracle_loop(ops, lib, case):
+    """The persistent kernel's n steps == n iterations of model.py:221-222 in the oracle:
+    key chains bit-exact, per-step loss rel 1e-5, parameters within 1e-3 * lr per step."""
+    n = 64
+    d, ds, tr, st, job = fused_setup(ops, lib, case, n)
+    assert ops.fused_supported(job) == 1
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), tr.key)
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), ds.key)
+    assert int(st["step"]) == n
+    got = st["loss"].cpu().numpy().astype(np.float64)
+    ref = np.array(tr.train_losses, np.float64)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
+    assert np.max(np.abs(st["P"].cpu().numpy() - tr.params)) <= n * 1e-3 * d.lr + 1e-7
+    assert relerr(st["M"].cpu().numpy(), tr.m) <= 1e-4
+    assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
+
+
+def test_fused_chunked_equals_single_launch(ops, lib):
+    """K steps in one launch == the same K steps split over launches (state fully carried)."""
+    case = FUSED_CASES[7]
+    _, _, _, a, ja = fused_setup(ops, lib, case, 50)
+    _, _, _, b, jb = fused_setup(ops, lib, case, 50)
+    sc = ops.fused_scratch(1)
+    ops.train_fused([ja], 50, sc)
+    torch.cuda.synchronize()
+    la = a["loss"].cpu().numpy().copy()
+    losses = []
+    for chunk in (1, 7, 42):
+        ops.train_fused([jb], chunk, sc)
+        torch.cuda.synchronize()
+        losses.append(b["loss"].cpu().numpy()[:chunk].copy())
+    np.testing.assert_array_equal(np.concatenate(losses).view(np.uint32), la.view(np.uint32))
+    for k in ("P", "M", "V", "mk", "dk", "step"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_fused_packed_equals_single(ops, lib):
+    """Packing many models into one launch does not change any of them (heterogeneous shapes)."""
+    n = 16
+    singles, packed, jobs = [], [], []
+    for case in FUSED_CASES:
+        _, _, _, st, job = fused_setup(ops, lib, case, n)
+        ops.train_fused([job], n, ops.fused_scratch(1))
+        singles.append(st)
+        _, _, _, st2, job2 = fused_setup(ops, lib, case, n)
+        packed.append(st2)
+        jobs.append(job2)
+    ops.train_fused(jobs, n, ops.fused_scratch(len(jobs)))
+    torch.cuda.synchronize()
+    for a, b in zip(singles, packed):
+        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_fused_fixed_variance_and_odd_batch(ops, lib):
+    for batch, tunable in ((100, False), (37, True), (33, False)):
+        case = FUSED_CASES[8]
+        n = 24
+        d, ds, tr, st, job = fused_setup(ops, lib, case, n, batch=batch, tunable=tunable)
+        ops.train_fused([job], n, ops.fused_scratch(1))
+        torch.cuda.synchronize()
+        tr.train(10 ** 9, start=0, stop=n, events=False)
+        np.testing.assert_array_equal(st["mk"].cpu().numpy(), tr.key)
+        np.testing.assert_array_equal(st["dk"].cpu().numpy(), ds.key)
+        got = st["loss"].cpu().numpy().astype(np.float64)
+        ref = np.array(tr.train_losses, np.float64)
+        assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
+        assert np.max(np.abs(st["P"].cpu().numpy() - tr.params)) <= n * 1e-3 * d.lr + 1e-7
+
+
+def test_fused_unsupported_shape_is_refused(ops, lib):
+    d = vs.VaeDesc(100, 9, 5)
+    P = torch.zeros(d.n_params, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    k = ops.key_tensor(jr.PRNGKey(0))
+    job = ops.make_job(odesc_to_c(lib, d), lib.make_data_desc("sphere", 4, 5), P, P.clone(), P.clone(), st, k, k.clone(),
+                       None, torch.zeros(4, device="cuda"))
+    assert ops.fused_supported(job) == 0
+    with pytest.raises(lib.VaeB200Error):
+        ops.train_fused([job], 4, ops.fused_scratch(1))

@@ -1,0 +1,78 @@
+"""Builds libvae_b200.so (sm_100a) in-tree with nvcc.  Run: python -m vae_training_b200.build
+
+Each .cu is compiled to an object in parallel, then linked; objects live in csrc/_obj/
+(git-ignored).  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libvae_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "vae_b200.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2",
+]
+
+
+def find_nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; libvae_b200.so cannot be built")
+    return nvcc
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime() -> float:
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER]
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(nvcc, src, obj, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return src, proc.returncode, proc.stdout + proc.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = find_nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hm = _headers_mtime()
+    todo, objs = [], []
+    for s in sources():
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hm):
+            todo.append((src, obj))
+    if todo:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
+            results = list(ex.map(lambda so: _compile(nvcc, so[0], so[1], verbose), todo))
+        for src, rc, out in results:
+            if verbose or rc != 0:
+                sys.stderr.write(out)
+            if rc != 0:
+                raise RuntimeError(f"nvcc failed on {src}")
+    if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError("nvcc failed linking libvae_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
