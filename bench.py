@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- VAE train-steps/sec (summed over packed models) on N B200s of one node.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  A "step" is one train step (one hot-loop iteration,
+model.py:221-222: dataset batch + key splits + eps draw + forward + ELBO + backward + Adam)
+of EVERY packed model; K steps run in one persistent launch.
+
+Workload (config.workload): BASELINE.json configs[1] -- the sigmoid padding VAE
+`sigmoid_vae_padding_expts.sh:1` (dd=3, pd=3 -> D=7, L=6, two decoders, B=100, lr 1e-4,
+eps0=-3, -tdv) -- packed as M independent runs per GPU that differ only in the dataset
+seed (the sweep's seed axis).  M models are sharded per rank with no communication
+("scaling": "weak").  `--workload` selects other single-Dense shapes of the sweeps;
+`--models 1` gives the literal single-model chain.
+
+--impl reference: the CPU oracle port (oracle/c, all host threads) on a bounded sample of
+the same workload.  The real reference (JAX/Flax) cannot be installed here: no jax/flax
+wheels, no network.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vae_train_steps_per_sec_summed_over_packed_models"
+UNIT = "train-steps/s"
+
+WORKLOADS = {
+    # name: (dataset, dd, pd, L, lr, eps0, first dataset seed, reference line)
+    "sigmoid_dd3_pd3_ld6": ("sigmoid", 3, 3, 6, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:1"),
+    "sigmoid_dd7_pd20_ld24": ("sigmoid", 7, 20, 24, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:6"),
+    "linear_dd3_pd9_ld20": ("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2, "seed_linpadding_expts.sh:1"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100000)
+    ap.add_argument("--warmup", type=int, default=2000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sigmoid_dd3_pd3_ld6", choices=sorted(WORKLOADS))
+    ap.add_argument("--models", type=int, default=0, help="models packed per GPU (0 = 148 SMs x resident CTAs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def make_specs(workload, n_models, first_index=0):
+    from vae_training_b200.packed import RunSpec
+    name, dd, pd, L, lr, eps0, seed0, _ = WORKLOADS[workload]
+    return [RunSpec(dataset=name, dataset_dimension=dd, padding_dim=pd, latent_dimension=L, learning_rate=lr,
+                    epsilon=eps0, tunable_decoder_var=True, dataset_seed=seed0 + first_index + i,
+                    name=f"{workload}_ds{seed0 + first_index + i}") for i in range(n_models)]
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------- CPU arms
+def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50):
+    """Times the C oracle port (oracle/c) on n_models independent runs; returns steps/s."""
+    from oracle import c_oracle as co
+    from oracle import datasets as ods
+    from oracle import jax_random as jr
+    from oracle import vae_step as vs
+    name, dd, pd, L, lr, eps0, seed0, _ = WORKLOADS[workload]
+    jobs = []
+    for i in range(n_models):
+        ds = ods.make_dataset(name, seed0 + i, dd, pd)
+        d = vs.VaeDesc(100, ds.ndim, L, sig_decoder=(name == "sigmoid"), epsilon0=eps0, lr=lr)
+        flat = vs.init_params(d, 0)
+        key = jr.PRNGKey(0)
+        _, key = jr.model_chain_next(key)
+        _, key = jr.model_chain_next(key)
+        ds.get_key()
+        jobs.append(co.Job(co.make_desc(d), co.make_data(name, dd, pd), flat, key, ds.key, ds.A, n_steps))
+    co.train_loop(jobs, warm_steps, n_threads)
+    t0 = time.perf_counter()
+    co.train_loop(jobs, n_steps, n_threads)
+    dt = time.perf_counter() - t0
+    assert all(np.isfinite(j.loss[:n_steps]).all() for j in jobs)
+    return n_models * n_steps / dt, dt
+
+
+def cpu_baseline(workload, target_seconds):
+    cores = os.cpu_count() or 1
+    n_models = cores
+    rate, _ = cpu_oracle_run(workload, n_models, 300, cores, warm_steps=20)       # calibrate
+    n_steps = max(200, int(rate * target_seconds / n_models))
+    rate, dt = cpu_oracle_run(workload, n_models, n_steps, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_models} independent {workload} runs x {n_steps} steps, oracle/c (plain C, float32, "
+                      f"AVX2) on {cores} threads, {dt:.1f} s; restated CPU oracle -- NOT the reference JAX runtime"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_models = cores
+    rate, _ = cpu_oracle_run(args.workload, n_models, 300, cores, warm_steps=20)
+    # each "step" of this arm = one train step of each of n_models models; bound the run to ~minutes
+    k = max(1, min(args.steps, int(rate * 20.0 / n_models)))
+    w = max(3, min(args.warmup, max(3, k // 10)))
+    rate, dt = cpu_oracle_run(args.workload, n_models, k, cores, warm_steps=w)
+    wl = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": w, "ms_per_step": dt / k * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} ({wl[7]}) x {n_models} independent runs on host cores",
+                       "batch": 100, "models": n_models},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_models} runs x {k} steps on {cores} threads (oracle/c); the reference's "
+                                       "JAX/Flax runtime is not installable here (no wheels, no network)"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from vae_training_b200 import init, ops
+    from vae_training_b200.packed import PackedRuns
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = int(args.steps), max(3, int(args.warmup))
+    n_models = args.models if args.models > 0 else 148 * 3
+    specs = make_specs(args.workload, n_models, first_index=rank * n_models)
+    runs = PackedRuns(specs, max_chunk=max(K, W))
+    states = [init.initial_state(s) for s in specs]
+    runs.upload(states)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # FFMA peak probe (roofline denominator for this on-chip, non-HBM, non-tensor kernel)
+    sink = torch.zeros(148 * 8 * 256, device="cuda")
+    ops.ffma_probe(148 * 8, 256, 2000, sink)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    flops = ops.ffma_probe(148 * 8, 256, 20000, sink)
+    e1.record()
+    torch.cuda.synchronize()
+    ffma_tflops = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    # ---- device-resident arm
+    runs.train_steps(W)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    runs.train_steps(K)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    loss_dev = runs.loss.view(n_models, runs.max_chunk)[:, :K]
+    if not bool(torch.isfinite(loss_dev).all()):
+        raise SystemExit("bench.py: non-finite loss in the timed region")
+    total_models = n_models * world
+    value = total_models * K / (ms * 1e-3)
+
+    # ---- end-to-end arm: host state in (pinned), fused steps, losses + state out
+    runs.train_host(states, W)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h2d = runs.upload(states)
+    runs.train_steps(K)
+    d2h = runs.download(K)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = total_models * K / (ms_e2e * 1e-3)
+    hl = runs.hloss[:n_models * K].numpy()
+    if not np.isfinite(hl).all():
+        raise SystemExit("bench.py: non-finite loss in the end-to-end region")
+
+    if rank == 0:
+        spec = specs[0]
+        wl = WORKLOADS[args.workload]
+        flop_step = spec.flops_per_step()
+        achieved = flop_step * (n_models * K) / (ms * 1e-3) / 1e12         # per GPU, algorithmic flops only
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "samples_per_sec": value * spec.batch_size,
+            "config": {"workload": f"{args.workload} ({wl[7]}; BASELINE.json configs[1] shape) x {n_models} "
+                                   f"independent dataset seeds packed per GPU", "batch": spec.batch_size,
+                       "models_per_gpu": n_models, "data_dim": spec.data_dim, "latent_dim": spec.latent_dimension,
+                       "l2_flush": "n/a: working set is SM-resident (shared memory); HBM traffic is the 4-byte "
+                                   "loss store per model-step",
+                       "parallelism": f"independent models x{world} GPUs, no collective"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                    "note": "PackedRuns.train_host: pinned host state -> device, K fused steps, per-step losses + "
+                            "final state -> host"},
+            "gpu_launches": 1,
+            "roofline": {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
+                         "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
+                         "traffic": None,
+                         "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one "
+                                 f"GPU; peak = FFMA probe measured in this run ({ffma_tflops:.1f} TFLOP/s); RNG work "
+                                 f"({spec.normals_per_step()} threefry normals/model-step) is not counted as flops",
+                         "normals_per_sec_per_gpu": spec.normals_per_step() * n_models * K / (ms * 1e-3)},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,244 @@
+"""Packed training of many independent VAE runs on one GPU (the sweep path).
+
+A ``PackedRuns`` object owns the device state of M models (parameters, Adam moments,
+step counters, carried PRNG keys, generator matrices, loss history) in a handful of flat
+device buffers and advances all of them with ONE persistent launch per chunk of steps
+(``vae_train_fused``, include/vae_b200.h).  It is the object ``bench.py`` times and the
+engine under ``vae.VAEModel.train`` / ``sweep.run_sweep``.
+
+Host <-> device contract of ``train_host`` (the end-to-end call): inputs are HOST arrays
+(initial parameters, keys, generator matrices); they are copied to the device from pinned
+memory, the fused kernel runs, and per-step losses plus the final state are copied back.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import VaeB200Error
+
+
+@dataclass
+class RunSpec:
+    """One model of a sweep: the flags of one ``python run.py ...`` line that shape the
+    hot path (run.py:10-38)."""
+    dataset: str                     # --dataset
+    dataset_dimension: int           # -dd
+    padding_dim: int                 # --padding_dim
+    latent_dimension: int            # --latent_dim
+    layer_sizes: Sequence[int] = ()          # --layer_sizes        (decoder hidden)
+    encoder_layer_sizes: Sequence[int] = ()  # --encoder_layer_sizes
+    batch_size: int = 100            # --batch_size
+    learning_rate: float = 1e-4      # -lr
+    epsilon: float = 0.0             # -e
+    tunable_decoder_var: bool = False  # -tdv
+    dataset_seed: int = 69           # -ds
+    dataset_intrinsic_dimension: int = 3  # -did
+    num_batches: int = 15000         # --num_batches
+    name: str = ""
+
+    @property
+    def data_dim(self) -> int:       # datasets.py:61,169,235
+        return self.dataset_dimension + self.padding_dim + (1 if self.dataset == "sigmoid" else 0)
+
+    def desc(self) -> _lib.VaeDesc:
+        return _lib.make_desc(self.batch_size, self.data_dim, self.latent_dimension, self.encoder_layer_sizes,
+                              self.layer_sizes, self.dataset == "sigmoid", self.tunable_decoder_var, self.epsilon,
+                              self.learning_rate)
+
+    def data_desc(self) -> _lib.VaeDataDesc:
+        return _lib.make_data_desc(self.dataset, self.dataset_dimension, self.padding_dim,
+                                   self.dataset_intrinsic_dimension)
+
+    def flops_per_step(self) -> int:
+        """per Dense fwd 2Bmn + dW 2Bmn + dX 2Bmn, no dX for the first
+        encoder layer."""
+        B = self.batch_size
+        es = [self.data_dim] + list(self.encoder_layer_sizes) + [self.latent_dimension]
+        ds = [self.latent_dimension] + list(self.layer_sizes) + [self.data_dim]
+        tot = sum((4 if i == 0 else 6) * B * es[i] * es[i + 1] for i in range(len(es) - 1))
+        tot += sum(6 * B * ds[i] * ds[i + 1] for i in range(len(ds) - 1)) * (2 if self.dataset == "sigmoid" else 1)
+        return tot
+
+    def normals_per_step(self) -> int:
+        g = self.dataset_intrinsic_dimension if self.dataset == "linear_gaussian" else self.dataset_dimension
+        return self.batch_size * (self.latent_dimension + self.data_dim + g)
+
+
+@dataclass
+class HostState:
+    """Host-side state of one model (what ``train_host`` takes and returns)."""
+    params: np.ndarray
+    adam_m: np.ndarray
+    adam_v: np.ndarray
+    step: int
+    model_key: np.ndarray            # uint32[2] carried model-side key
+    dataset_key: np.ndarray          # uint32[2] carried dataset-side key
+    A: Optional[np.ndarray]          # generator matrix (None for sphere)
+    losses: List[np.ndarray] = field(default_factory=list)
+
+
+def _offsets(sizes, align=4):
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (int(s) + align - 1) // align * align
+    return offs, o
+
+
+class PackedRuns:
+    def __init__(self, specs: Sequence[RunSpec], max_chunk: int, device="cuda"):
+        if not specs:
+            raise VaeB200Error("PackedRuns needs at least one run")
+        self.specs = list(specs)
+        self.M = len(self.specs)
+        self.device = torch.device(device)
+        self.max_chunk = int(max_chunk)
+        self.descs = [s.desc() for s in self.specs]
+        self.datas = [s.data_desc() for s in self.specs]
+        self.n_params = [ops.param_count(d) for d in self.descs]
+        self.p_off, ptot = _offsets(self.n_params)
+        a_sizes = [self._a_size(s) for s in self.specs]
+        self.a_sizes = a_sizes
+        self.a_off, atot = _offsets(a_sizes)
+        dev = self.device
+        # flat device buffers (16-byte aligned slices per model)
+        self.P = torch.zeros(ptot, dtype=torch.float32, device=dev)
+        self.Mo = torch.zeros(ptot, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(ptot, dtype=torch.float32, device=dev)
+        self.A = torch.zeros(max(atot, 4), dtype=torch.float32, device=dev)
+        self.step = torch.zeros(self.M * 4, dtype=torch.int32, device=dev)        # stride 4: 16-byte slots
+        self.keys = torch.zeros(self.M * 8, dtype=torch.uint32, device=dev)       # [model_key(2) pad(2) dataset_key(2) pad(2)]
+        self.loss = torch.zeros(self.M * self.max_chunk, dtype=torch.float32, device=dev)
+        self.scratch = ops.fused_scratch(self.M, dev)
+        # pinned host mirrors for the end-to-end path
+        pin = torch.cuda.is_available()
+        self.hP = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
+        self.hM = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
+        self.hV = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
+        self.hA = torch.zeros(max(atot, 4), dtype=torch.float32, pin_memory=pin)
+        self.hstep = torch.zeros(self.M * 4, dtype=torch.int32, pin_memory=pin)
+        self.hkeys = torch.zeros(self.M * 8, dtype=torch.uint32, pin_memory=pin)
+        self.hloss = torch.zeros(self.M * self.max_chunk, dtype=torch.float32, pin_memory=pin)
+        self.jobs = [self._make_job(i) for i in range(self.M)]
+        unsupported = [i for i, j in enumerate(self.jobs) if ops.fused_supported(j) == 0]
+        if unsupported:
+            s = self.specs[unsupported[0]]
+            raise VaeB200Error(f"run {unsupported[0]} ({s.dataset} dd={s.dataset_dimension} pd={s.padding_dim} "
+                               f"L={s.latent_dimension} hidden={list(s.layer_sizes)}) has no fused kernel")
+
+    @staticmethod
+    def _a_size(s: RunSpec) -> int:
+        if s.dataset == "linear_gaussian":
+            return s.dataset_dimension * s.dataset_intrinsic_dimension
+        if s.dataset == "sigmoid":
+            return s.dataset_dimension
+        return 0
+
+    # views -----------------------------------------------------------------
+    def params(self, i):
+        return self.P[self.p_off[i]:self.p_off[i] + self.n_params[i]]
+
+    def adam_m(self, i):
+        return self.Mo[self.p_off[i]:self.p_off[i] + self.n_params[i]]
+
+    def adam_v(self, i):
+        return self.V[self.p_off[i]:self.p_off[i] + self.n_params[i]]
+
+    def gen_matrix(self, i):
+        return self.A[self.a_off[i]:self.a_off[i] + self.a_sizes[i]] if self.a_sizes[i] else None
+
+    def step_of(self, i):
+        return self.step[4 * i:4 * i + 1]
+
+    def model_key(self, i):
+        return self.keys[8 * i:8 * i + 2]
+
+    def dataset_key(self, i):
+        return self.keys[8 * i + 4:8 * i + 6]
+
+    def losses(self, i, n):
+        return self.loss[i * self.max_chunk:i * self.max_chunk + n]
+
+    def _make_job(self, i):
+        return ops.make_job(self.descs[i], self.datas[i], self.params(i), self.adam_m(i), self.adam_v(i),
+                            self.step_of(i), self.model_key(i), self.dataset_key(i), self.gen_matrix(i),
+                            self.losses(i, self.max_chunk))
+
+    # state movement ----------------------------------------------------------
+    def _stage(self, states: Sequence[HostState]):
+        hP, hM, hV, hA = self.hP.numpy(), self.hM.numpy(), self.hV.numpy(), self.hA.numpy()
+        hs, hk = self.hstep.numpy(), self.hkeys.numpy()
+        for i, st in enumerate(states):
+            o, n = self.p_off[i], self.n_params[i]
+            hP[o:o + n] = st.params
+            hM[o:o + n] = st.adam_m
+            hV[o:o + n] = st.adam_v
+            if self.a_sizes[i]:
+                hA[self.a_off[i]:self.a_off[i] + self.a_sizes[i]] = np.asarray(st.A, np.float32).ravel()
+            hs[4 * i] = st.step
+            hk[8 * i:8 * i + 2] = st.model_key
+            hk[8 * i + 4:8 * i + 6] = st.dataset_key
+
+    def upload(self, states: Sequence[HostState]) -> int:
+        """Host -> device copy of every model's state (async on the current stream).
+        Returns the number of bytes copied."""
+        if len(states) != self.M:
+            raise VaeB200Error("upload: one HostState per run is required")
+        self._stage(states)
+        nb = 0
+        for d, h in ((self.P, self.hP), (self.Mo, self.hM), (self.V, self.hV), (self.A, self.hA),
+                     (self.step, self.hstep), (self.keys, self.hkeys)):
+            d.copy_(h, non_blocking=True)
+            nb += h.numel() * h.element_size()
+        return nb
+
+    def download(self, n_loss: int, states: Optional[Sequence[HostState]] = None) -> int:
+        """Device -> host copy of losses[:n_loss] per model and the full state.  Synchronises
+        the current stream when ``states`` is given (values are unpacked into them)."""
+        nb = 0
+        pairs = [(self.hP, self.P), (self.hM, self.Mo), (self.hV, self.V), (self.hstep, self.step), (self.hkeys, self.keys)]
+        for h, d in pairs:
+            h.copy_(d, non_blocking=True)
+            nb += h.numel() * h.element_size()
+        if n_loss > 0:
+            src = self.loss.view(self.M, self.max_chunk)[:, :n_loss]
+            if n_loss != self.max_chunk:
+                src = src.contiguous()               # compact on the device, then one flat copy
+            self.hloss[:self.M * n_loss].copy_(src.reshape(-1), non_blocking=True)
+            nb += self.M * n_loss * 4
+        if states is not None:
+            torch.cuda.current_stream().synchronize()
+            hP, hM, hV = self.hP.numpy(), self.hM.numpy(), self.hV.numpy()
+            hs, hk = self.hstep.numpy(), self.hkeys.numpy()
+            hl = self.hloss[:self.M * max(n_loss, 1)].view(self.M, max(n_loss, 1)).numpy()
+            for i, st in enumerate(states):
+                o, n = self.p_off[i], self.n_params[i]
+                st.params = hP[o:o + n].copy()
+                st.adam_m = hM[o:o + n].copy()
+                st.adam_v = hV[o:o + n].copy()
+                st.step = int(hs[4 * i])
+                st.model_key = hk[8 * i:8 * i + 2].copy()
+                st.dataset_key = hk[8 * i + 4:8 * i + 6].copy()
+                if n_loss > 0:
+                    st.losses.append(hl[i, :n_loss].copy())
+        return nb
+
+    # compute -----------------------------------------------------------------
+    def train_steps(self, n_steps: int):
+        """n_steps iterations of the hot loop (model.py:221-222) for every packed model, in
+        one persistent launch on the current stream.  Losses land in ``losses(i, n_steps)``."""
+        if n_steps > self.max_chunk:
+            raise VaeB200Error(f"n_steps={n_steps} exceeds max_chunk={self.max_chunk}")
+        ops.train_fused(self.jobs, n_steps, self.scratch)
+
+    def train_host(self, states: Sequence[HostState], n_steps: int):
+        """End-to-end: host state in, n_steps fused steps, host state + losses out."""
+        h2d = self.upload(states)
+        self.train_steps(n_steps)
+        d2h = self.download(n_steps, states)
+        return h2d, d2h
