@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VAE_B200_ABI_VERSION 1
+#define VAE_B200_ABI_VERSION 2
 #define VAE_MAX_HIDDEN 8
 
 enum {
@@ -55,9 +55,14 @@ typedef struct VaeDesc {
   int32_t dec_hidden[VAE_MAX_HIDDEN];
   int32_t sig_decoder;                /* dataset_name == "sigmoid"  networks.py:75  */
   int32_t tunable_decoder_var;        /* -tdv                       networks.py:70  */
-  float epsilon0;                     /* --epsilon                  run.py:32       */
-  float lr;                           /* -lr                        run.py:15       */
-  float beta1, beta2, adam_eps;       /* flax.optim.Adam defaults .9 .999 1e-8      */
+  int32_t reserved_;                  /* keeps the doubles 8-byte aligned           */
+  /* Hyper-parameters are doubles because the reference holds them as Python floats:
+   * legacy flax evaluates (1 - beta) in double before rounding to float32, and the
+   * kernels reproduce that: b = (float)beta, 1-b = (float)(1.0 - beta),
+   * bias correction 1 - powf((float)beta, t). */
+  double epsilon0;                    /* --epsilon                  run.py:32       */
+  double lr;                          /* -lr                        run.py:15       */
+  double beta1, beta2, adam_eps;      /* flax.optim.Adam defaults .9 .999 1e-8      */
 } VaeDesc;
 
 /* Flat parameter layout (params, adam_m, adam_v and gradients all use it):

@@ -144,7 +144,8 @@ static float loss_and_grad(const OrDesc* d, const Lay* L, Work* w, const float* 
   const int B = d->batch, Ld = d->latent_dim, D = d->data_dim, ldz = Ld + D;
   const float fB = (float)B;
   const float* lv = P + L->off_lv;
-  const float e = d->tunable_decoder_var ? P[L->off_eps] * d->epsilon0 : d->epsilon0;
+  const float eps0 = (float)d->epsilon0;
+  const float e = d->tunable_decoder_var ? P[L->off_eps] * eps0 : eps0;
   const float sd = expf(0.5f * e), var = expf(e);
   mlp_fwd(&L->enc, P, x, D, w->enc_act, B);
   const float* mu = w->enc_act[L->enc.n - 1];
@@ -180,7 +181,7 @@ static float loss_and_grad(const OrDesc* d, const Lay* L, Work* w, const float* 
   const float dkl = (-0.5f * klc * fB + 0.5f * (float)s_mu2) / fB;
   const float mse = (0.5f * (float)s_r2 / var + 0.5f * (LOG_2PI + e) * fB * (float)D) / fB;
   if (d->tunable_decoder_var)
-    G[L->off_eps] = d->epsilon0 * (-0.5f * (float)s_r2 / var + 0.5f * fB * (float)D + 0.5f * sd * (float)s_rz / var) / fB;
+    G[L->off_eps] = eps0 * (-0.5f * (float)s_r2 / var + 0.5f * fB * (float)D + 0.5f * sd * (float)s_rz / var) / fB;
   mlp_bwd(&L->dec, P, G, w->zs, Ld, w->dec_act, w->dxh, w->ga, w->gb, w->dzs, 0, B);
   if (L->has_sig) mlp_bwd(&L->sig, P, G, w->zs, Ld, w->sig_act, w->dpre, w->ga, w->gb, w->dzs, 1, B);
   for (int l = 0; l < Ld; ++l) {
@@ -195,13 +196,16 @@ static float loss_and_grad(const OrDesc* d, const Lay* L, Work* w, const float* 
 }
 
 static void adam(const OrDesc* d, int64_t n, float* P, float* M, float* V, int32_t* step, const float* G) {
-  const double t = (double)(step[0] + 1);
-  const float bc1 = (float)(1.0 - pow((double)d->beta1, t)), bc2 = (float)(1.0 - pow((double)d->beta2, t));
-  const float b1 = d->beta1, b2 = d->beta2, lr = d->lr, eps = d->adam_eps;
+  /* legacy flax.optim.Adam [3P]: Python-float hyper-parameters; (1 - beta) is evaluated in
+   * double and rounded, beta ** t is a float32 power of the float32 beta */
+  const float t = (float)(step[0] + 1);
+  const float b1 = (float)d->beta1, b2 = (float)d->beta2, lr = (float)d->lr, eps = (float)d->adam_eps;
+  const float omb1 = (float)(1.0 - d->beta1), omb2 = (float)(1.0 - d->beta2);
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
   for (int64_t i = 0; i < n; ++i) {
     const float g = G[i];
-    const float m = b1 * M[i] + (1.f - b1) * g;
-    const float v = b2 * V[i] + (1.f - b2) * g * g;
+    const float m = b1 * M[i] + omb1 * g;
+    const float v = b2 * V[i] + omb2 * g * g;
     M[i] = m; V[i] = v;
     P[i] = P[i] - lr * (m / bc1) / (sqrtf(v / bc2) + eps);
   }

@@ -18,8 +18,8 @@ typedef struct OrDesc {            /* same field order as VaeDesc in include/vae
   int32_t batch, data_dim, latent_dim;
   int32_t n_enc_hidden, enc_hidden[OR_MAX_HIDDEN];
   int32_t n_dec_hidden, dec_hidden[OR_MAX_HIDDEN];
-  int32_t sig_decoder, tunable_decoder_var;
-  float epsilon0, lr, beta1, beta2, adam_eps;
+  int32_t sig_decoder, tunable_decoder_var, reserved_;
+  double epsilon0, lr, beta1, beta2, adam_eps;   /* Python floats in the reference */
 } OrDesc;
 
 typedef struct OrData { int32_t kind, dim, padding_dim, intrinsic_dim; } OrData;  /* 0 sphere 1 linear 2 sigmoid */

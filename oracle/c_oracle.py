@@ -20,9 +20,9 @@ class OrDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("data_dim", C.c_int32), ("latent_dim", C.c_int32),
                 ("n_enc_hidden", C.c_int32), ("enc_hidden", C.c_int32 * MAXH),
                 ("n_dec_hidden", C.c_int32), ("dec_hidden", C.c_int32 * MAXH),
-                ("sig_decoder", C.c_int32), ("tunable_decoder_var", C.c_int32),
-                ("epsilon0", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("adam_eps", C.c_float)]
+                ("sig_decoder", C.c_int32), ("tunable_decoder_var", C.c_int32), ("reserved_", C.c_int32),
+                ("epsilon0", C.c_double), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("adam_eps", C.c_double)]
 
 
 class OrData(C.Structure):

@@ -250,8 +250,10 @@ def adam_update(desc: VaeDesc, flat, m, v, step, grad, dtype=np.float32):
     updates already applied (starts at 0); returns new (flat, m, v, step+1)."""
     dt = dtype
     b1, b2 = dt(desc.beta1), dt(desc.beta2)
-    m = b1 * m + (dt(1) - b1) * grad
-    v = b2 * v + (dt(1) - b2) * np.square(grad)
+    # hyper-parameters are Python floats in the reference: (1 - beta) is evaluated in double
+    # and then rounded to the array dtype; beta ** t is a power in the array dtype
+    m = b1 * m + dt(1.0 - desc.beta1) * grad
+    v = b2 * v + dt(1.0 - desc.beta2) * np.square(grad)
     t = dt(step + 1)
     m_hat = m / (dt(1) - b1 ** t)
     v_hat = v / (dt(1) - b2 ** t)

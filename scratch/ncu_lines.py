@@ -1,0 +1,71 @@
+"""Attribute ncu SASS-level samples to CUDA source lines (via nvdisasm -g line markers).
+usage: python scratch/ncu_lines.py <rep> <cubin> <kernel-substr> [top]"""
+import csv, re, subprocess, sys, collections
+rep, cubin, kname = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+h = rows[hdr]
+ci = {n: h.index(n) for n in ("Source", "# Samples", "Instructions Executed")}
+sass = [(r[ci["Source"]].strip(), int(r[ci["# Samples"]] or 0), int(r[ci["Instructions Executed"]] or 0)) for r in rows[hdr + 1:] if len(r) > ci["Instructions Executed"]]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+# find function section
+start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l]
+lines = []
+cur = None
+infn = False
+for l in dis:
+    if l.startswith(".text."):
+        infn = kname in l
+        continue
+    if not infn:
+        continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        cur = (m.group(1).split("/")[-1], int(m.group(2)))
+        continue
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
+        lines.append(cur)
+print("sass instrs", len(sass), "disasm instrs", len(lines))
+n = min(len(sass), len(lines))
+by_line = collections.defaultdict(lambda: [0, 0])
+for (ins, smp, ex), ln in zip(sass[:n], lines[:n]):
+    by_line[ln][0] += smp
+    by_line[ln][1] += ex
+tot_s = sum(v[0] for v in by_line.values()); tot_e = sum(v[1] for v in by_line.values())
+print("total samples", tot_s, "total warp-instr", tot_e)
+src_cache = {}
+def src(ln):
+    if ln is None: return ""
+    f, n = ln
+    import glob
+    if f not in src_cache:
+        c = glob.glob(f"/root/repo/vae_training_b200/csrc/{f}")
+        src_cache[f] = open(c[0]).read().splitlines() if c else []
+    s = src_cache[f]
+    return s[n - 1].strip()[:90] if 0 < n <= len(s) else ""
+for ln, (s, e) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{str(ln):28s} samples {100*s/tot_s:5.1f}%  instr {100*e/tot_e:5.1f}%  | {src(ln)}")
+# ---- region summary
+reg = collections.defaultdict(lambda: [0, 0])
+def region(ln):
+    if ln is None: return "none"
+    f, n = ln
+    if f == "common.cuh":
+        if n <= 57: return "threefry"
+        if n <= 110: return "log1p"
+        if n <= 135: return "erfinv+normal"
+        if n <= 157: return "det_exp/sigmoid"
+        return "warp_sum"
+    if f == "fused_small.cu":
+        if n < 197: return "init"
+        if n < 229: return "phaseA-loop/idx"
+        if n < 357: return "phaseB"
+        if n < 440: return "phaseC"
+        return "store"
+    return f
+for ln, (s, e) in by_line.items():
+    r = region(ln); reg[r][0] += s; reg[r][1] += e
+for r, (s, e) in sorted(reg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{r:22s} samples {100*s/tot_s:5.1f}%  instr {100*e/tot_e:5.1f}%  warp-instr/CTA-step {e/ (444*2000):8.1f}")

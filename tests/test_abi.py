@@ -41,15 +41,15 @@ def test_no_torch_types_or_cxx_mangling_in_abi(lib):
 
 
 def test_struct_layout_matches_header(lib):
-    # VaeDesc: 3 + 1 + 8 + 1 + 8 + 2 int32, 5 floats
-    assert C.sizeof(lib.VaeDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 2 + 5)
+    # VaeDesc: 3 + 1 + 8 + 1 + 8 + 2 + 1 int32, 5 doubles
+    assert C.sizeof(lib.VaeDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 2 + 1) + 8 * 5
     assert C.sizeof(lib.VaeDataDesc) == 16
     assert C.sizeof(lib.VaeTrainJob) == C.sizeof(lib.VaeDesc) + 16 + 9 * 8
 
 
 def test_host_side_helpers(lib):
     L = lib.load()
-    assert L.vae_abi_version() == 1
+    assert L.vae_abi_version() == 2
     d = lib.make_desc(100, 7, 6, sig_decoder=True)
     assert L.vae_param_count(C.byref(d)) == 153
     h = (200, 200, 200)

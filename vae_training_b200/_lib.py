@@ -25,9 +25,9 @@ class VaeDesc(C.Structure):
         ("batch", C.c_int32), ("data_dim", C.c_int32), ("latent_dim", C.c_int32),
         ("n_enc_hidden", C.c_int32), ("enc_hidden", C.c_int32 * VAE_MAX_HIDDEN),
         ("n_dec_hidden", C.c_int32), ("dec_hidden", C.c_int32 * VAE_MAX_HIDDEN),
-        ("sig_decoder", C.c_int32), ("tunable_decoder_var", C.c_int32),
-        ("epsilon0", C.c_float), ("lr", C.c_float), ("beta1", C.c_float),
-        ("beta2", C.c_float), ("adam_eps", C.c_float),
+        ("sig_decoder", C.c_int32), ("tunable_decoder_var", C.c_int32), ("reserved_", C.c_int32),
+        ("epsilon0", C.c_double), ("lr", C.c_double), ("beta1", C.c_double),
+        ("beta2", C.c_double), ("adam_eps", C.c_double),
     ]
 
 

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2",
-]
+] + (["-DVAE_FUSED_DEBUG"] if os.environ.get("VAE_FUSED_DEBUG") else [])
 
 
 def find_nvcc() -> str:

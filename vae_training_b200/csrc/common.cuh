@@ -163,6 +163,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Float32 Adam constants derived from the double hyper-parameters the way legacy flax
+// does (see VaeDesc in include/vae_b200.h).
+struct AdamHyper { float lr, b1, b2, omb1, omb2, eps; };
+inline AdamHyper make_adam_hyper(const VaeDesc* d) {
+  AdamHyper h;
+  h.lr = (float)d->lr; h.b1 = (float)d->beta1; h.b2 = (float)d->beta2;
+  h.omb1 = (float)(1.0 - d->beta1); h.omb2 = (float)(1.0 - d->beta2); h.eps = (float)d->adam_eps;
+  return h;
+}
+
 // Host-side shape helpers (api.cu).
 struct Layout {
   int n_enc, n_dec;                 // number of Dense layers per net

@@ -27,7 +27,8 @@ struct FusedJobDev {
   float* params; float* adam_m; float* adam_v; int32_t* step;
   uint32_t* model_key; uint32_t* dataset_key; const float* A; float* loss_out;
   int32_t batch; int32_t tunable; int32_t shape_id; int32_t pad_;
-  float eps0, lr, b1, b2, adam_eps;
+  float eps0, lr, b1, b2, omb1, omb2, adam_eps;
+  float* dbg;
 };
 
 __host__ __device__ constexpr int up4(int n) { return (n + 3) & ~3; }
@@ -354,10 +355,17 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
       }
     }
     __syncthreads();
+#ifdef VAE_FUSED_DEBUG
+    if (s == 0 && job.dbg) {
+      for (int i = t; i < y.total; i += kT) job.dbg[i] = sm[i];
+      if (t == 0) { int* q = (int*)(job.dbg + y.total); q[0] = y.z; q[1] = y.gn; q[2] = y.xs; q[3] = y.zs; q[4] = y.dx; q[5] = y.dm; q[6] = y.red; q[7] = y.P; }
+    }
+    __syncthreads();
+#endif
     // ================= phase C: one thread per parameter: gradient + Adam
     {
       b1t *= (double)job.b1; b2t *= (double)job.b2;
-      const float ibc1 = (float)(1.0 / (1.0 - b1t)), ibc2 = (float)(1.0 / (1.0 - b2t));
+      const float ibc1 = 1.0f / (1.0f - (float)b1t), ibc2 = 1.0f / (1.0f - (float)b2t);
       const float e = sm[y.scal + 4 * slot], sd = sm[y.scal + 4 * slot + 1], inv_var = sm[y.scal + 4 * slot + 2];
       const float s_mu2 = (sm[y.red + 0] + sm[y.red + 1]) + (sm[y.red + 2] + sm[y.red + 3]);
       const float s_r2 = (sm[y.red + 4] + sm[y.red + 5]) + (sm[y.red + 6] + sm[y.red + 7]);
@@ -398,8 +406,8 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
         } else if (kind == 2) {   // d loss / d epsilon (param): eps0 * dL/de
           g = job.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
         }
-        const float m = job.b1 * M[poff] + (1.f - job.b1) * g;
-        const float v = job.b2 * V[poff] + (1.f - job.b2) * g * g;
+        const float m = job.b1 * M[poff] + job.omb1 * g;
+        const float v = job.b2 * V[poff] + job.omb2 * g * g;
         M[poff] = m; V[poff] = v;
         newp[k] = P[poff] - job.lr * (m * ibc1) / (sqrtf(v * ibc2) + job.adam_eps);
       }
@@ -540,9 +548,10 @@ int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, vo
     vae::FusedJobDev& o = host[i];
     o.params = j.params; o.adam_m = j.adam_m; o.adam_v = j.adam_v; o.step = j.step;
     o.model_key = j.model_key; o.dataset_key = j.dataset_key; o.A = j.A; o.loss_out = j.loss_out;
-    o.batch = j.desc.batch; o.tunable = j.desc.tunable_decoder_var; o.shape_id = id; o.pad_ = 0;
-    o.eps0 = j.desc.epsilon0; o.lr = j.desc.lr; o.b1 = j.desc.beta1; o.b2 = j.desc.beta2;
-    o.adam_eps = j.desc.adam_eps;
+    o.batch = j.desc.batch; o.tunable = j.desc.tunable_decoder_var; o.shape_id = id; o.pad_ = 0; o.dbg = (float*)j.workspace;
+    const vae::AdamHyper hp = vae::make_adam_hyper(&j.desc);
+    o.eps0 = (float)j.desc.epsilon0; o.lr = hp.lr; o.b1 = hp.b1; o.b2 = hp.b2; o.omb1 = hp.omb1; o.omb2 = hp.omb2;
+    o.adam_eps = hp.eps;
   }
   // pageable-source async copies are staged before the call returns, so `host` may be freed
   cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * sizeof(vae::FusedJobDev),

@@ -246,16 +246,16 @@ latent_grad_kernel(float* __restrict__ dzs, const float* __restrict__ mu, const 
 // Legacy flax.optim.Adam.apply_param_gradient [3P].
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-            const float* __restrict__ g, const int32_t* __restrict__ step, int64_t n, float lr,
-            float b1, float b2, float eps) {
+            const float* __restrict__ g, const int32_t* __restrict__ step, int64_t n, AdamHyper hp) {
   const double t = (double)(step[0] + 1);
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2 = (float)(1.0 - pow((double)b2, t));
+  const float bc1 = 1.0f - (float)pow((double)hp.b1, t);     // 1 - powf(b, t), correctly rounded
+  const float bc2 = 1.0f - (float)pow((double)hp.b2, t);
+  const float b1 = hp.b1, b2 = hp.b2, lr = hp.lr, eps = hp.eps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float mi = b1 * m[i] + hp.omb1 * gi;
+    const float vi = b2 * v[i] + hp.omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     const float mh = mi / bc1, vh = vi / bc2;
@@ -370,12 +370,13 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   }
   const int Ld = desc->latent_dim, D = desc->data_dim, ldz = Ld + D;
   const float inv_bs = 1.0f / (float)scale_rows;
+  const float eps0 = (float)desc->epsilon0;
   const float* lv = params + L.off_eps_p;
   const float* eps_ptr;
   float eps_mul;
   if (mode == MODE_SAMPLE) { eps_ptr = d_cur_eps; eps_mul = 1.f; }
-  else if (desc->tunable_decoder_var) { eps_ptr = params + L.off_eps; eps_mul = desc->epsilon0; }
-  else { eps_ptr = nullptr; eps_mul = desc->epsilon0; }
+  else if (desc->tunable_decoder_var) { eps_ptr = params + L.off_eps; eps_mul = eps0; }
+  else { eps_ptr = nullptr; eps_mul = eps0; }
   float* part_mu2 = w.part;
   float* part_r2 = w.part + kMaxPart;
   float* part_rz = w.part + 2 * kMaxPart;
@@ -457,7 +458,7 @@ int vae_adam_update(const VaeDesc* desc, float* params, float* adam_m, float* ad
   int64_t blocks = (L.n_params + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   vae::adam_kernel<<<(int)blocks, 256, 0, s>>>(params, adam_m, adam_v, d_grad, d_step, L.n_params,
-                                               desc->lr, desc->beta1, desc->beta2, desc->adam_eps);
+                                               vae::make_adam_hyper(desc));
   VAE_LAUNCH_OK("adam_kernel");
   vae::step_inc_kernel<<<1, 1, 0, s>>>(d_step);
   VAE_LAUNCH_OK("step_inc_kernel");

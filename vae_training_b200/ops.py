@@ -169,6 +169,8 @@ def vae_sample(desc: VaeDesc, params, z, rows: int, current_epsilon, ws: Workspa
 
 def make_job(desc: VaeDesc, data: VaeDataDesc, params, adam_m, adam_v, step, model_key, dataset_key, A,
              loss_out, workspace=None) -> VaeTrainJob:
+    """The job records raw device pointers; the caller keeps every tensor alive (and
+    unmoved) until the launches that use the job have completed."""
     j = VaeTrainJob()
     j.desc = desc
     j.data = data
