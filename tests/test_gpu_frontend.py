@@ -1,0 +1,117 @@
+"""GPU tests of the host-side mirror of the reference interface (datasets.py, vae.py,
+run.py, sweep.py): the full train() schedule with eval / plot events against the oracle
+trainer, packed sweeps, output files."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import datasets as ods
+from oracle import trainer as otr
+from oracle import vae_step as vs
+
+pytestmark = pytest.mark.gpu
+
+
+def build_pair(name, dd, pd, L, hidden, N, seed=69, lr=1e-4, eps0=-3.0, n_print=8, n_plot=16, eval_batch=50):
+    from vae_training_b200 import datasets, vae
+    cls = {"sphere": datasets.SphereDataset, "sigmoid": datasets.SigmoidDataset}
+    if name == "linear_gaussian":
+        ds = datasets.LinearGaussianDataset(seed, dimension=dd, intrinsic_dimension=3, padding_dimension=pd)
+    else:
+        ds = cls[name](seed, dimension=dd, padding_dimension=pd)
+    ods_ = ods.make_dataset(name, seed, dd, pd)
+    if ods_.A is not None:
+        np.testing.assert_array_equal(ds.A.cpu().numpy().reshape(ods_.A.shape), ods_.A)
+    hid = [int(v) for v in hidden.split("|")] if hidden else []
+    d = vs.VaeDesc(100, ods_.ndim, L, hid, hid, sig_decoder=(name == "sigmoid"), epsilon0=eps0, lr=lr)
+    flat = vs.init_params(d, 0)
+    m = vae.VAEModel(None, N, 1, 100, lr, hidden, hidden, None, None, eps0, False, ds, L, tunable_decoder_var=True,
+                     dataset_name=name, initial_params=flat, verbose=False)
+    m.n_print, m.n_plot, m.print_batch_size, m.plot_batch_size = n_print, n_plot, eval_batch, eval_batch
+    tr = otr.OracleTrainer(d, ods_, flat, n_print=n_print, n_plot=n_plot, eval_batch=eval_batch, dtype=np.float64)
+    return m, tr, ods_
+
+
+def compare(m, tr, ods_, N):
+    got = m.vae_losses.astype(np.float64)
+    ref = np.array(tr.vae_losses, np.float64)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-5
+    np.testing.assert_array_equal(m.key.cpu().numpy(), tr.key)
+    np.testing.assert_array_equal(m.dataset.key.cpu().numpy(), ods_.key)
+    assert len(m.var_enc) == len(tr.var_enc)
+    for a, b in zip(m.var_enc, tr.var_enc):
+        np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-4, atol=1e-6)
+    for a, b in zip(m.var_dec, tr.var_dec):
+        np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-4, atol=1e-6)
+    assert set(m.stats) == set(tr.stats)
+    for k in tr.stats:
+        np.testing.assert_allclose(np.array(m.stats[k], np.float64), np.array(tr.stats[k], np.float64), rtol=2e-4, atol=1e-6)
+    assert int(m.step) == N
+
+
+@pytest.mark.parametrize("name,dd,pd,L,hidden", [("sigmoid", 3, 3, 6, ""), ("linear_gaussian", 3, 9, 20, ""),
+                                                 ("sphere", 3, 3, 6, "24|16")])
+def test_train_schedule_matches_oracle(name, dd, pd, L, hidden):
+    """model.py:207-222 end to end (fused path for the single-Dense shapes, per-op path for
+    the hidden-layer one): interleaved train/eval losses, learned variances, stats, key chains."""
+    N = 30
+    m, tr, ods_ = build_pair(name, dd, pd, L, hidden, N, seed=2 if name == "linear_gaussian" else 69)
+    assert m.fused == (hidden == "")
+    m.train_distribution(save=False)
+    tr.train(N)
+    compare(m, tr, ods_, N)
+
+
+def test_train_many_equals_individual_runs():
+    from vae_training_b200 import vae
+    cfgs = [("sigmoid", 3, 3, 6, "", 30), ("sigmoid", 5, 5, 10, "", 22), ("linear_gaussian", 6, 6, 20, "", 17)]
+    packed = [build_pair(*c[:5], c[5]) for c in cfgs]
+    vae.train_many([p[0] for p in packed], save=False)
+    for (m, tr, ods_), c in zip(packed, cfgs):
+        tr.train(c[5])
+        compare(m, tr, ods_, c[5])
+
+
+def test_sweep_outputs(tmp_path, monkeypatch):
+    from vae_training_b200 import run, sweep, vae
+    monkeypatch.setattr(run, "DATA_DIR", str(tmp_path))
+    monkeypatch.setattr(vae.VAEModel, "n_print", 10)
+    monkeypatch.setattr(vae.VAEModel, "n_plot", 20)
+    script = tmp_path / "expts.sh"
+    script.write_text(
+        'python run.py s1 --dataset sigmoid --encoder_layer_sizes "" --layer_sizes "" -ow --latent_dim 6 --padding_dim 3 -dd 3 --num_batches 25 --epsilon -3 -tdv\n'
+        'python run.py l1 --dataset linear_gaussian --encoder_layer_sizes "" --layer_sizes "" -ow --latent_dim 20 --padding_dim 9 -dd 3 --num_batches 25 --epsilon -1 -tdv -ds 2 -lr 1e-3\n')
+    models = sweep.run_sweep(sweep.parse_script(str(script)))
+    assert len(models) == 2
+    for name in ("s1", "l1"):
+        d = tmp_path / name
+        assert sorted(os.listdir(d)) == ["args.json", "losses.npz", "model.pkl"]
+        z = np.load(d / "losses.npz", allow_pickle=True)
+        for k in ("VAE Loss", "Decoder Variance", "Encoder Variance", "EigenValues", "Average Log Likelihood",
+                  "Correlation Ratio", "KL divergence", "mse"):
+            assert k in z.files, k
+        assert z["VAE Loss"].shape == (25 + 3,)          # N train losses + one per stats event (vae.py:130,136)
+        assert z["Encoder Variance"].shape[0] == 3 and np.isfinite(z["VAE Loss"]).all()
+    import pickle
+    sd = pickle.load(open(tmp_path / "s1" / "model.pkl", "rb"))
+    assert sd["state"]["step"] == 25 and "SigDecoder" in sd["target"]["params"]
+
+
+def test_dataset_classes_follow_reference_interface():
+    from vae_training_b200 import datasets
+    ds = datasets.SphereDataset(69, dimension=3, padding_dimension=3)
+    assert ds.shape == (6,) and ds.dimension == 6 and ds.is_epochs is False
+    k0 = ds.key.clone()
+    b, lat = ds.get_batch(100, return_latents=True)
+    assert lat is None and b.shape == (100, 6) and not torch.equal(k0, ds.key)
+    sc = ds.score_batch(b)
+    assert set(sc) == {"Sphere Error", "Padding Error"} and sc["Sphere Error"] < 1e-10 and sc["Padding Error"] == 0
+    ref = ods.SphereDataset(69, 3, 3).get_batch(100)
+    np.testing.assert_array_equal(b.cpu().numpy(), ref)
+    noisy = datasets.LinearGaussianDataset(2, dimension=3, intrinsic_dimension=3, padding_dimension=2, var_added=0.25)
+    ref2 = ods.LinearGaussianDataset(2, 3, 3, 2, var_added=0.25)
+    np.testing.assert_allclose(noisy.get_batch(50).cpu().numpy(), ref2.get_batch(50), rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(noisy.key.cpu().numpy(), ref2.key)
