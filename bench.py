@@ -192,7 +192,13 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = int(args.steps), max(3, int(args.warmup))
-    n_models = args.models if args.models > 0 else 148 * 3
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    if args.models > 0:
+        n_models = args.models
+    else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
+        probe = PackedRuns(make_specs(args.workload, 1), max_chunk=4)
+        n_models = n_sm * max(1, ops.fused_ctas_per_sm(probe.jobs[0]))
+        del probe
     specs = make_specs(args.workload, n_models, first_index=rank * n_models)
     runs = PackedRuns(specs, max_chunk=max(K, W))
     states = [init.initial_state(s) for s in specs]

@@ -174,6 +174,9 @@ typedef struct VaeTrainJob {
  * kernel, 2 = thread-block-cluster kernel), else 0. */
 int vae_train_fused_supported(const VaeTrainJob* job);
 size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job);
+/* Resident CTAs (= models) per SM of the job's fused kernel on the current device: the
+ * pack size that fills the GPU is this x the SM count.  0 if unsupported, <0 on error. */
+int vae_train_fused_ctas_per_sm(const VaeTrainJob* job);
 /* Device scratch the launch needs for its job table. */
 size_t vae_train_fused_scratch_bytes(int32_t n_jobs);
 /* jobs: HOST array of n_jobs descriptors, all of the same vae_train_fused_supported()

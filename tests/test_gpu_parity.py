@@ -214,11 +214,12 @@ def test_train_steps_vs_oracle(ops, lib, name):
 
 @pytest.mark.parametrize("name", ["sphere_21_16_h200", "sigmoid_28_24", "wide_batch"])
 def test_train_steps_well_conditioned_all_params(ops, lib, name):
-    """Same as above with adam_eps = 1e-3 (>> float32 gradient noise): the m/sqrt(v)
+    """Same as above with adam_eps = 1.0 (>> the absolute float32 gradient noise, which is
+    ~1e-5 x max|g| and max|g| is O(10..100) here because 1/var_d = e^3): the m/sqrt(v)
     normalisation no longer amplifies rounding noise, so EVERY parameter must stay within
     1e-3 * lr per step of the float64 oracle."""
     import dataclasses
-    d = dataclasses.replace(STEP_CASES[name], adam_eps=1e-3)
+    d = dataclasses.replace(STEP_CASES[name], adam_eps=1.0)
     cd = odesc_to_c(lib, d)
     flat, _, _ = make_inputs(d)
     P = dev(flat)

@@ -56,6 +56,27 @@ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t&
   x0 += k2; x1 += k0 + 5u;
 }
 
+// Two independent blocks interleaved statement by statement (ILP for latency-bound callers).
+#define VAE_TF_ROUND2(r)   \
+  a0 += a1; b0 += b1;      \
+  a1 = rotl32(a1, r); b1 = rotl32(b1, r); \
+  a1 ^= a0; b1 ^= b0;
+__device__ __forceinline__ void threefry2x32_x2(uint32_t ka0, uint32_t ka1, uint32_t& a0, uint32_t& a1,
+                                                uint32_t kb0, uint32_t kb1, uint32_t& b0, uint32_t& b1) {
+  const uint32_t ka2 = ka0 ^ ka1 ^ 0x1BD11BDAu, kb2 = kb0 ^ kb1 ^ 0x1BD11BDAu;
+  a0 += ka0; a1 += ka1; b0 += kb0; b1 += kb1;
+  VAE_TF_ROUND2(13) VAE_TF_ROUND2(15) VAE_TF_ROUND2(26) VAE_TF_ROUND2(6)
+  a0 += ka1; a1 += ka2 + 1u; b0 += kb1; b1 += kb2 + 1u;
+  VAE_TF_ROUND2(17) VAE_TF_ROUND2(29) VAE_TF_ROUND2(16) VAE_TF_ROUND2(24)
+  a0 += ka2; a1 += ka0 + 2u; b0 += kb2; b1 += kb0 + 2u;
+  VAE_TF_ROUND2(13) VAE_TF_ROUND2(15) VAE_TF_ROUND2(26) VAE_TF_ROUND2(6)
+  a0 += ka0; a1 += ka1 + 3u; b0 += kb0; b1 += kb1 + 3u;
+  VAE_TF_ROUND2(17) VAE_TF_ROUND2(29) VAE_TF_ROUND2(16) VAE_TF_ROUND2(24)
+  a0 += ka1; a1 += ka2 + 4u; b0 += kb1; b1 += kb2 + 4u;
+  VAE_TF_ROUND2(13) VAE_TF_ROUND2(15) VAE_TF_ROUND2(26) VAE_TF_ROUND2(6)
+  a0 += ka2; a1 += ka0 + 5u; b0 += kb2; b1 += kb0 + 5u;
+}
+
 // random.split(key): rows (y0[0], y0[1]) and (y1[0], y1[1]) of blocks (0,2), (1,3).
 __device__ __forceinline__ void split2(uint32_t k0, uint32_t k1, uint32_t row0[2], uint32_t row1[2]) {
   uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;
@@ -132,6 +153,42 @@ __device__ __forceinline__ float normal_from_bits(uint32_t bits) {
   const float f = __fsub_rn(__uint_as_float((bits >> 9) | 0x3F800000u), 1.0f);
   const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));
   return __fmul_rn(1.41421354f, erf_inv_f32(u));
+}
+
+// Same values as normal_from_bits, bit for bit; the tail polynomial (|z| >~ 2.93, 0.34% of
+// draws) is taken through a warp-uniform branch so the common path carries no selects and
+// no IEEE sqrt.
+__device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
+  const float lo = -0.99999994f;
+  const float f = __fsub_rn(__uint_as_float((bits >> 9) | 0x3F800000u), 1.0f);
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));
+  const float w = neg_log1p_neg(__fmul_rn(u, u));
+  float p;
+  if (__all_sync(__activemask(), w < 5.0f)) {
+    const float ww = __fsub_rn(w, 2.5f);
+    p = 2.81022636e-08f;
+    p = __fadd_rn(__fmul_rn(p, ww), 3.43273939e-07f);
+    p = __fadd_rn(__fmul_rn(p, ww), -3.5233877e-06f);
+    p = __fadd_rn(__fmul_rn(p, ww), -4.39150654e-06f);
+    p = __fadd_rn(__fmul_rn(p, ww), 0.00021858087f);
+    p = __fadd_rn(__fmul_rn(p, ww), -0.00125372503f);
+    p = __fadd_rn(__fmul_rn(p, ww), -0.00417768164f);
+    p = __fadd_rn(__fmul_rn(p, ww), 0.246640727f);
+    p = __fadd_rn(__fmul_rn(p, ww), 1.50140941f);
+  } else {
+    const bool central = w < 5.0f;
+    const float ww = central ? __fsub_rn(w, 2.5f) : __fsub_rn(__fsqrt_rn(w), 3.0f);
+    p = central ? 2.81022636e-08f : -0.000200214257f;
+    p = __fadd_rn(__fmul_rn(p, ww), central ? 3.43273939e-07f : 0.000100950558f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? -3.5233877e-06f : 0.00134934322f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? -4.39150654e-06f : -0.00367342844f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? 0.00021858087f : 0.00573950773f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00125372503f : -0.0076224613f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00417768164f : 0.00943887047f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? 0.246640727f : 1.00167406f);
+    p = __fadd_rn(__fmul_rn(p, ww), central ? 1.50140941f : 2.83297682f);
+  }
+  return __fmul_rn(1.41421354f, __fmul_rn(p, u));
 }
 
 // Deterministic exp / sigmoid for the generators (mirrors oracle/datasets.py:det_expf).

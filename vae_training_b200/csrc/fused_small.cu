@@ -14,29 +14,41 @@
 // kernel rows d >= DR receive a gradient of exactly 0 and Adam leaves them (and their
 // zero moments) bit-for-bit unchanged; those rows are never loaded.
 //
-// Per step: phase A (all threads) threefry + normal draws into smem; phase B (thread per
-// batch row) generator transform, forward, loss partials, backward to dmu; phase C
-// (thread per parameter) dW = sum_b h*d, Adam.  Two CTA barriers per step.
+// Per step (two CTA barriers):
+//   phase A (all threads)        threefry blocks -> normals -> eps (B, L+D) and generator
+//                                normals (B, g) in smem; lanes 0-3 advance the key chains
+//   phase B (thread per row)     generator transform, forward, loss partials, backward to
+//                                dmu; operands of the weight gradients are stored
+//                                TRANSPOSED ([feature][batch], batch contiguous)
+//   phase C (thread per tile)    dW tiles (TI x TJ) = sum_b h[i][b] d[j][b] with 128-bit
+//                                loads along the batch, split-K over KS adjacent lanes,
+//                                shuffle reduce, Adam, publish new weights
 #include "common.cuh"
 
 namespace vae {
 
 constexpr int kT = 128;
+#ifndef VAE_SMALL_MAXB
+#define VAE_SMALL_MAXB 6
+#endif
 
 struct FusedJobDev {
   float* params; float* adam_m; float* adam_v; int32_t* step;
   uint32_t* model_key; uint32_t* dataset_key; const float* A; float* loss_out;
   int32_t batch; int32_t tunable; int32_t shape_id; int32_t pad_;
   float eps0, lr, b1, b2, omb1, omb2, adam_eps;
-  float* dbg;
 };
 
 __host__ __device__ constexpr int up4(int n) { return (n + 3) & ~3; }
 __host__ __device__ constexpr int oddi(int n) { return n | 1; }
+__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+// batch stride of the transposed operand arrays: a multiple of 4 floats whose quarter is
+// odd, so 128-bit loads of 8 different feature rows hit 8 different bank groups
+__host__ __device__ inline int batch_stride(int B) { int g = (B + 3) / 4; g |= 1; return 4 * g; }
 
-template <int D_, int L_, int DR_, bool SIG_, int KIND_, int G_>
+template <int D_, int L_, int DR_, bool SIG_, int KIND_, int G_, int TI_, int TJ_>
 struct SmallCfg {
-  static constexpr int D = D_, L = L_, DR = DR_, KIND = KIND_, G = G_;
+  static constexpr int D = D_, L = L_, DR = DR_, KIND = KIND_, G = G_, TI = TI_, TJ = TJ_;
   static constexpr bool SIG = SIG_;
   static constexpr int DD = KIND == VAE_DATA_SIGMOID ? DR - 1 : DR;   // generator -dd
   static constexpr int LP = up4(L), DP = up4(D);
@@ -51,34 +63,49 @@ struct SmallCfg {
   static constexpr int oEp = oLv + LP;                   // [4]   epsilon
   static constexpr int PP = oEp + 4;
   static constexpr int NDEC = SIG ? 2 : 1;
-  static constexpr int NA = DR * L + L + (L * D + D) * NDEC + L + 1;   // active params
-  static constexpr int NPT = (NA + kT - 1) / kT;
+  static constexpr int NFLAT = D * L + L + (L * D + D) * NDEC + L;   // + 1 if tunable
   static constexpr int AN = KIND == VAE_DATA_LINEAR_GAUSSIAN ? DD * G : (KIND == VAE_DATA_SIGMOID ? DD : 0);
-  // activation row strides (odd => row-per-thread accesses are bank-conflict free)
-  static constexpr int SZ = oddi(L + D), SG = oddi(G), SX = oddi(DR), SL = oddi(L), SD = oddi(D);
-  // smem layout in floats given B rows
+  // row-major activation strides (odd => row-per-thread accesses are bank-conflict free)
+  static constexpr int SZ = oddi(L + D), SG = oddi(G);
+  // gradient segments: (h rows I) x (d rows J); the last h row is the all-ones row, i.e.
+  // the bias gradient.  seg 0: [x;1] x dmu, seg 1: [zs;1] x dxhat, seg 2: [zs;1] x dpre,
+  // seg 3: [1] x (dzs*z1)  (epsilon_p)
+  static constexpr int I0 = DR + 1, J0 = L, I1 = L + 1, J1 = D, I3 = 1, J3 = L;
+  static constexpr int nJ0 = cdiv(J0, TJ), nJ1 = cdiv(J1, TJ), nJ3 = cdiv(J3, TJ);
+  static constexpr int T0 = cdiv(I0, TI) * nJ0, T1 = cdiv(I1, TI) * nJ1, T2 = SIG ? T1 : 0, T3 = nJ3;
+  static constexpr int NT = T0 + T1 + T2 + T3;
+  static constexpr int KS = NT * 8 <= kT ? 8 : NT * 4 <= kT ? 4 : NT * 2 <= kT ? 2 : 1;
+  static constexpr int NTASK = NT * KS;
+  static constexpr int ROUNDS = cdiv(NTASK, kT);
+  static constexpr int EPL = cdiv(TI * TJ, KS);          // tile elements updated per lane
+  // CTAs per SM the per-shape kernel is compiled for (register cap), from the shared-memory
+  // footprint at the reference batch size 100
+  static constexpr int SMEM100 = 4 * (3 * PP + 4 * LP + 32 + up4(AN + 1) + 8 + up4(100 * SZ) + up4(100 * SG) +
+                                      (DR + 1 + L + 1 + 2 * L + D * NDEC) * 100) + 1024;
+  static constexpr int MINB_RAW = (227 * 1024) / SMEM100;
+  static constexpr int MINB = MINB_RAW < 1 ? 1 : MINB_RAW > VAE_SMALL_MAXB ? VAE_SMALL_MAXB : MINB_RAW;
   struct Lay {
-    int P, M, V, sl, el, kt, scal, one, red, A, keys, desc, z, gn, xs, zs, dx, dp, dm, q, total;
+    int P, M, V, sl, el, kt, scal, red, A, keys, z, gn, hx, hz, dm, dx, dp, q, total, BP;
   };
   __host__ __device__ static Lay layout(int B) {
     Lay y; int o = 0;
+    const int BP = batch_stride(B);
+    y.BP = BP;
     y.P = o; o += PP; y.M = o; o += PP; y.V = o; o += PP;
     y.sl = o; o += LP; y.el = o; o += LP;
     y.kt = o; o += 2 * LP;         // [2 slots][LP]  1 + lv - e^lv (KL term of the loss)
     y.scal = o; o += 8;            // [2 slots][e, sd, inv_var, -]
-    y.one = o; o += 4;             // 1.0f (the "h" of bias-like gradients)
     y.red = o; o += 16;            // [3][4] warp partials
     y.A = o; o += up4(AN + 1);
     y.keys = o; o += 8;            // uint32 [2 slots][lat0 lat1 bat0 bat1]
-    y.desc = o; o += NPT * kT * 2; // int2 per (k, thread)
     y.z = o; o += up4(B * SZ);
     y.gn = o; o += up4(B * SG);
-    y.xs = o; o += up4(B * SX);
-    y.zs = o; o += up4(B * SL);
-    y.dx = o; o += up4(B * SD);
-    y.dp = o; o += SIG ? up4(B * SD) : 0;
-    y.dm = o; o += up4(B * SL);
-    y.q = o; o += up4(B * SL);
+    y.hx = o; o += (DR + 1) * BP;  // transposed from here on: [feature][BP]
+    y.hz = o; o += (L + 1) * BP;
+    y.dm = o; o += L * BP;
+    y.dx = o; o += D * BP;
+    y.dp = o; o += SIG ? D * BP : 0;
+    y.q = o; o += L * BP;
     y.total = o;
     return y;
   }
@@ -102,52 +129,25 @@ struct SmallCfg {
     g -= L;
     return (tunable && g == 0) ? oEp : -1;
   }
-  static constexpr int NFLAT = D * L + L + (L * D + D) * NDEC + L;   // + 1 if tunable
 };
 
-// descriptor packing: .x = h_off | d_off << 16 ; .y = poff | h_str << 16 | d_str << 23 | kind << 30
-__device__ __forceinline__ int2 pack_desc(int h_off, int h_str, int d_off, int d_str, int poff, int kind) {
-  return make_int2(h_off | (d_off << 16), poff | (h_str << 16) | (d_str << 23) | (kind << 30));
-}
-
-template <class C>
-__device__ __forceinline__ int2 make_desc(int a, const typename C::Lay& y, bool tunable) {
-  constexpr int D = C::D, L = C::L, DR = C::DR;
-  const int ones = y.one;
-  if (a < DR * L) { const int i = a / L, j = a - i * L; return pack_desc(y.xs + i, C::SX, y.dm + j, C::SL, C::oWe + i * C::LP + j, 0); }
-  a -= DR * L;
-  if (a < L) return pack_desc(ones, 0, y.dm + a, C::SL, C::oBe + a, 0);
-  a -= L;
-  if (a < L * D) { const int i = a / D, j = a - i * D; return pack_desc(y.zs + i, C::SL, y.dx + j, C::SD, C::oWd + i * C::DP + j, 0); }
-  a -= L * D;
-  if (a < D) return pack_desc(ones, 0, y.dx + a, C::SD, C::oBd + a, 0);
-  a -= D;
-  if constexpr (C::SIG) {
-    if (a < L * D) { const int i = a / D, j = a - i * D; return pack_desc(y.zs + i, C::SL, y.dp + j, C::SD, C::oWs + i * C::DP + j, 0); }
-    a -= L * D;
-    if (a < D) return pack_desc(ones, 0, y.dp + a, C::SD, C::oBs + a, 0);
-    a -= D;
-  }
-  if (a < L) return pack_desc(ones, 0, y.q + a, C::SL, C::oLv + a, 1);
-  a -= L;
-  if (a == 0 && tunable) return pack_desc(ones, 0, ones, 0, C::oEp, 2);
-  return pack_desc(ones, 0, ones, 0, 0, 3);     // kind 3: nothing to do
-}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 template <class C>
 __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* sm) {
   constexpr int D = C::D, L = C::L, DR = C::DR, DD = C::DD, G = C::G, LP = C::LP, DP = C::DP;
+  constexpr int TI = C::TI, TJ = C::TJ, KS = C::KS;
   constexpr int LD = L + D;
   const int t = threadIdx.x;
   const int B = job.batch;
   const bool tunable = job.tunable != 0;
   const typename C::Lay y = C::layout(B);
+  const int BP = y.BP, NG = BP >> 2;
   float* P = sm + y.P; float* M = sm + y.M; float* V = sm + y.V;
   uint32_t* keys = reinterpret_cast<uint32_t*>(sm + y.keys);
-  int2* desc = reinterpret_cast<int2*>(sm + y.desc);
 
   // ---- load state
-  for (int i = t; i < 3 * C::PP; i += kT) sm[y.P + i] = 0.f;
+  for (int i = t; i < y.total; i += kT) sm[i] = 0.f;
   __syncthreads();
   const int nflat = C::NFLAT + (tunable ? 1 : 0);
   for (int g = t; g < nflat; g += kT) {
@@ -155,9 +155,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     if (o >= 0) { P[o] = job.params[g]; M[o] = job.adam_m[g]; V[o] = job.adam_v[g]; }
   }
   for (int i = t; i < C::AN; i += kT) sm[y.A + i] = job.A[i];
-#pragma unroll
-  for (int k = 0; k < C::NPT; ++k) desc[k * kT + t] = make_desc<C>(k * kT + t, y, tunable);
-  if (t == 0) sm[y.one] = 1.0f;
+  for (int b = t; b < B; b += kT) { sm[y.hx + DR * BP + b] = 1.0f; sm[y.hz + L * BP + b] = 1.0f; }   // ones rows
   __syncthreads();
   // Derived per-step constants are double-buffered by step parity: phase B/C of step s
   // read slot s&1, the owning thread publishes the post-update values into the other slot.
@@ -170,7 +168,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     const float e = tunable ? P[C::oEp] * job.eps0 : job.eps0;
     for (int q = 0; q < 2; ++q) { sm[y.scal + 4 * q] = e; sm[y.scal + 4 * q + 1] = expf(0.5f * e); sm[y.scal + 4 * q + 2] = expf(-e); }
   }
-  // Adam bias-correction powers (double running products: error ~ t * 1e-16)
+  // Adam bias-correction powers (double running products of the float32 betas)
   const int32_t step0 = job.step[0];
   double b1t = pow((double)job.b1, (double)step0), b2t = pow((double)job.b2, (double)step0);
 
@@ -198,29 +196,49 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
   const float invB = 1.0f / (float)B;
   const int half_e = (B * LD + 1) >> 1, n_e = B * LD;
   const int half_d = (B * G + 1) >> 1, n_d = B * G;
+  const int n_blocks = half_e + half_d;
 
   for (int64_t s = 0; s < n_steps; ++s) {
     const int slot = (int)(s & 1);
-    // ================= phase A: random draws
+    // ================= phase A: random draws (two independent threefry blocks in flight)
     {
       const uint32_t lk0 = keys[slot * 4 + 0], lk1 = keys[slot * 4 + 1];
       const uint32_t bk0 = keys[slot * 4 + 2], bk1 = keys[slot * 4 + 3];
       if (t < 4 && s + 1 < n_steps) advance_keys(slot ^ 1);
       float* z = sm + y.z; float* gn = sm + y.gn;
-      for (int w = t; w < half_e + half_d; w += kT) {
-        if (w < half_e) {
-          const int j = w, j2 = w + half_e;
-          uint32_t x0 = (uint32_t)j, x1 = j2 < n_e ? (uint32_t)j2 : 0u;
-          threefry2x32(lk0, lk1, x0, x1);
-          { const int r = j / LD; z[r * C::SZ + (j - r * LD)] = normal_from_bits(x0); }
-          if (j2 < n_e) { const int r = j2 / LD; z[r * C::SZ + (j2 - r * LD)] = normal_from_bits(x1); }
-        } else {
-          const int j = w - half_e, j2 = j + half_d;
-          uint32_t x0 = (uint32_t)j, x1 = j2 < n_d ? (uint32_t)j2 : 0u;
-          threefry2x32(bk0, bk1, x0, x1);
-          { const int r = j / G; gn[r * C::SG + (j - r * G)] = normal_from_bits(x0); }
-          if (j2 < n_d) { const int r = j2 / G; gn[r * C::SG + (j2 - r * G)] = normal_from_bits(x1); }
+      // flat element index -> offset in the row-padded array (divisions by constants)
+      auto off_of = [](bool eps, int j) -> int {
+        const int oe = C::SZ == LD ? j : (j / LD) * C::SZ + j % LD;
+        const int od = C::SG == G ? j : (j / G) * C::SG + j % G;
+        return eps ? oe : od;
+      };
+      for (int w0 = t; w0 < n_blocks; w0 += 2 * kT) {
+        uint32_t xa[2], xb[2];
+        int ja[2], jb[2];          // element indices (negative: no store)
+        float* dst[2]; bool iseps[2];
+        uint32_t ka[2], kb[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int w = w0 + u * kT;
+          const bool valid = w < n_blocks;
+          const bool eps = w < half_e;
+          const int j = eps ? w : w - half_e;
+          const int half = eps ? half_e : half_d;
+          const int n = eps ? n_e : n_d;
+          ka[u] = eps ? lk0 : bk0; kb[u] = eps ? lk1 : bk1;
+          dst[u] = eps ? z : gn; iseps[u] = eps;
+          xa[u] = (uint32_t)j;
+          xb[u] = (j + half < n) ? (uint32_t)(j + half) : 0u;
+          ja[u] = valid ? j : -1;
+          jb[u] = (valid && j + half < n) ? j + half : -1;
         }
+        threefry2x32_x2(ka[0], kb[0], xa[0], xb[0], ka[1], kb[1], xa[1], xb[1]);
+        const float n0 = normal_from_bits_fast(xa[0]), n1 = normal_from_bits_fast(xb[0]);
+        const float n2 = normal_from_bits_fast(xa[1]), n3 = normal_from_bits_fast(xb[1]);
+        if (ja[0] >= 0) dst[0][off_of(iseps[0], ja[0])] = n0;
+        if (jb[0] >= 0) dst[0][off_of(iseps[0], jb[0])] = n1;
+        if (ja[1] >= 0) dst[1][off_of(iseps[1], ja[1])] = n2;
+        if (jb[1] >= 0) dst[1][off_of(iseps[1], jb[1])] = n3;
       }
     }
     __syncthreads();
@@ -234,14 +252,14 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
         const float* gr = sm + y.gn + b * C::SG;
         // ---- generator transform (bit-exact with oracle/datasets.py)
         float x[DR];
-        if (C::KIND == VAE_DATA_SPHERE) {
+        if constexpr (C::KIND == VAE_DATA_SPHERE) {
           float acc = 0.f;
 #pragma unroll
           for (int j = 0; j < DD; ++j) { x[j] = gr[j]; const float sq = __fmul_rn(x[j], x[j]); acc = j == 0 ? sq : __fadd_rn(acc, sq); }
           const float rad = __fsqrt_rn(acc);
 #pragma unroll
           for (int j = 0; j < DD; ++j) x[j] = __fdiv_rn(x[j], rad);
-        } else if (C::KIND == VAE_DATA_LINEAR_GAUSSIAN) {
+        } else if constexpr (C::KIND == VAE_DATA_LINEAR_GAUSSIAN) {
           const float* A = sm + y.A;
 #pragma unroll
           for (int i = 0; i < DD; ++i) {
@@ -257,9 +275,9 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
           for (int j = 0; j < DD; ++j) { x[j] = gr[j]; const float pr = __fmul_rn(x[j], A[j]); acc = j == 0 ? pr : __fadd_rn(acc, pr); }
           x[DD] = det_sigmoid(acc);
         }
-        float* xrow = sm + y.xs + b * C::SX;
+        float* hxc = sm + y.hx + b;
 #pragma unroll
-        for (int d = 0; d < DR; ++d) xrow[d] = x[d];
+        for (int d = 0; d < DR; ++d) hxc[d * BP] = x[d];
         // ---- encoder: mu = x We + be   (only the DR non-padding columns contribute)
         float mu[LP];
 #pragma unroll
@@ -287,12 +305,12 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
             sp[4 * q] = u.x; sp[4 * q + 1] = u.y; sp[4 * q + 2] = u.z; sp[4 * q + 3] = u.w;
           }
         }
-        float* zsrow = sm + y.zs + b * C::SL;
+        float* hzc = sm + y.hz + b;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           kl_acc = fmaf(mu[l], mu[l], kl_acc);
           const float zsl = fmaf(sm[y.sl + l], zr[l], mu[l]);
-          zsrow[l] = zsl;
+          hzc[l * BP] = zsl;
 #pragma unroll
           for (int q = 0; q < DP / 4; ++q) {
             const float4 w = *reinterpret_cast<const float4*>(P + C::oWd + l * DP + 4 * q);
@@ -306,30 +324,30 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
           }
         }
         // ---- output, residual, d x_hat  (dec[] becomes d x_hat, sp[] becomes d sig_pre)
-        float* dxrow = sm + y.dx + b * C::SD;
-        float* dprow = sm + y.dp + b * C::SD;
+        float* dxc = sm + y.dx + b;
+        float* dpc = sm + y.dp + b;
 #pragma unroll
         for (int d = 0; d < DP; ++d) {
           if (d < D) {
             const float z2 = zr[L + d];
             float xh = dec[d];
             float sg = 0.f;
-            if constexpr (C::SIG) { sg = 1.f / (1.f + expf(-sp[d])); xh += sg; }
+            if constexpr (C::SIG) { sg = fast_sigmoid(sp[d]); xh += sg; }
             xh = fmaf(z2, sd, xh);
             const float r = xh - (d < DR ? x[d < DR ? d : 0] : 0.f);
             r2_acc = fmaf(r, r, r2_acc);
             rz_acc = fmaf(r, z2, rz_acc);
             const float g = r * gscale;
-            dec[d] = g; dxrow[d] = g;
-            if constexpr (C::SIG) { const float gp = g * sg * (1.f - sg); sp[d] = gp; dprow[d] = gp; }
+            dec[d] = g; dxc[d * BP] = g;
+            if constexpr (C::SIG) { const float gp = g * sg * (1.f - sg); sp[d] = gp; dpc[d * BP] = gp; }
           } else {
             dec[d] = 0.f;
             if constexpr (C::SIG) sp[d] = 0.f;
           }
         }
         // ---- dzs = dxhat Wd^T (+ dpre Ws^T); dmu = dzs + mu/B; q = dzs * z1
-        float* dmrow = sm + y.dm + b * C::SL;
-        float* qrow = sm + y.q + b * C::SL;
+        float* dmc = sm + y.dm + b;
+        float* qc = sm + y.q + b;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           float a0 = 0.f, a1 = 0.f;
@@ -345,8 +363,8 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
             }
           }
           const float dz = a0 + a1;
-          dmrow[l] = fmaf(mu[l], invB, dz);
-          qrow[l] = dz * zr[l];
+          dmc[l * BP] = fmaf(mu[l], invB, dz);
+          qc[l * BP] = dz * zr[l];
         }
       }
       kl_acc = warp_sum(kl_acc); r2_acc = warp_sum(r2_acc); rz_acc = warp_sum(rz_acc);
@@ -355,14 +373,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
       }
     }
     __syncthreads();
-#ifdef VAE_FUSED_DEBUG
-    if (s == 0 && job.dbg) {
-      for (int i = t; i < y.total; i += kT) job.dbg[i] = sm[i];
-      if (t == 0) { int* q = (int*)(job.dbg + y.total); q[0] = y.z; q[1] = y.gn; q[2] = y.xs; q[3] = y.zs; q[4] = y.dx; q[5] = y.dm; q[6] = y.red; q[7] = y.P; }
-    }
-    __syncthreads();
-#endif
-    // ================= phase C: one thread per parameter: gradient + Adam
+    // ================= phase C: gradient tiles + Adam
     {
       b1t *= (double)job.b1; b2t *= (double)job.b2;
       const float ibc1 = 1.0f / (1.0f - (float)b1t), ibc2 = 1.0f / (1.0f - (float)b2t);
@@ -371,67 +382,109 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
       const float s_r2 = (sm[y.red + 4] + sm[y.red + 5]) + (sm[y.red + 6] + sm[y.red + 7]);
       const float s_rz = (sm[y.red + 8] + sm[y.red + 9]) + (sm[y.red + 10] + sm[y.red + 11]);
       const float fB = (float)B;
-      if (t == 32) {   // loss = mean_b(Dkl + mse)   (networks.py:94-98)
+      auto adam = [&](int poff, float g) -> float {
+        const float m = job.b1 * M[poff] + job.omb1 * g;
+        const float v = job.b2 * V[poff] + job.omb2 * g * g;
+        M[poff] = m; V[poff] = v;
+        const float p = P[poff] - job.lr * (m * ibc1) / (sqrtf(v * ibc2) + job.adam_eps);
+        P[poff] = p;
+        return p;
+      };
+      if (t == kT - 1) {   // loss = mean_b(Dkl + mse) (networks.py:94-98); epsilon parameter
         float klc = 0.f;
 #pragma unroll
         for (int l = 0; l < L; ++l) klc += sm[y.kt + slot * LP + l];
         const float dkl = (-0.5f * klc * fB + 0.5f * s_mu2) * invB;
         const float mse = (0.5f * inv_var * s_r2 + 0.5f * (1.8378770664093453f + e) * fB * (float)D) * invB;
         job.loss_out[s] = dkl + mse;
-      }
-      float newp[C::NPT]; int newo[C::NPT]; int newk[C::NPT];
-#pragma unroll
-      for (int k = 0; k < C::NPT; ++k) {
-        const int2 dsc = desc[k * kT + t];
-        const int h_off = dsc.x & 0xFFFF, d_off = (dsc.x >> 16) & 0xFFFF;
-        const int poff = dsc.y & 0xFFFF, h_str = (dsc.y >> 16) & 0x7F, d_str = (dsc.y >> 23) & 0x7F;
-        const int kind = (dsc.y >> 30) & 3;
-        newk[k] = kind; newo[k] = poff; newp[k] = 0.f;
-        if (kind == 3) continue;
-        const float* hp = sm + h_off; const float* dp = sm + d_off;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int b = kind == 2 ? B : 0;
-        for (; b + 4 <= B; b += 4) {
-          a0 = fmaf(hp[0], dp[0], a0);
-          a1 = fmaf(hp[h_str], dp[d_str], a1);
-          a2 = fmaf(hp[2 * h_str], dp[2 * d_str], a2);
-          a3 = fmaf(hp[3 * h_str], dp[3 * d_str], a3);
-          hp += 4 * h_str; dp += 4 * d_str;
-        }
-        for (; b < B; ++b) { a0 = fmaf(hp[0], dp[0], a0); hp += h_str; dp += d_str; }
-        float g = (a0 + a1) + (a2 + a3);
-        if (kind == 1) {          // d loss / d epsilon_p[l]
-          const int l = poff - C::oLv;
-          g = g * 0.5f * sm[y.sl + l] - 0.5f * (1.f - sm[y.el + l]);
-        } else if (kind == 2) {   // d loss / d epsilon (param): eps0 * dL/de
-          g = job.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
-        }
-        const float m = job.b1 * M[poff] + job.omb1 * g;
-        const float v = job.b2 * V[poff] + job.omb2 * g * g;
-        M[poff] = m; V[poff] = v;
-        newp[k] = P[poff] - job.lr * (m * ibc1) / (sqrtf(v * ibc2) + job.adam_eps);
-      }
-      // Phase C reads activations, this thread's own P/M/V/sl/el entries and the
-      // slot-parity constants only, so new values can be published without a barrier.
-#pragma unroll
-      for (int k = 0; k < C::NPT; ++k) {
-        if (newk[k] == 3) continue;
-        P[newo[k]] = newp[k];
-        if (newk[k] == 1) {
-          const int l = newo[k] - C::oLv;
-          const float elv = expf(newp[k]);
-          sm[y.sl + l] = expf(0.5f * newp[k]); sm[y.el + l] = elv;
-          sm[y.kt + (slot ^ 1) * LP + l] = 1.f + newp[k] - elv;
-        }
-        if (newk[k] == 2) {
-          const float e2 = newp[k] * job.eps0;
+        if (tunable) {     // d loss / d epsilon (param) = eps0 * dL/de
+          const float g = job.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
+          const float e2 = adam(C::oEp, g) * job.eps0;
           float* sc = sm + y.scal + 4 * (slot ^ 1);
           sc[0] = e2; sc[1] = expf(0.5f * e2); sc[2] = expf(-e2);
         }
       }
+#pragma unroll 1
+      for (int rnd = 0; rnd < C::ROUNDS; ++rnd) {
+        if (rnd * kT + (t & ~31) >= C::NTASK) break;                    // warp-uniform
+        const int gt = rnd * kT + t;
+        const bool valid = gt < C::NTASK;
+        const int task = valid ? gt : C::NTASK - 1;
+        const int tile = task / KS, ks = task % KS;
+        // decode segment
+        int seg, loc;
+        if (tile < C::T0) { seg = 0; loc = tile; }
+        else if (tile < C::T0 + C::T1) { seg = 1; loc = tile - C::T0; }
+        else if (tile < C::T0 + C::T1 + C::T2) { seg = 2; loc = tile - C::T0 - C::T1; }
+        else { seg = 3; loc = tile - C::T0 - C::T1 - C::T2; }
+        const int nJ = seg == 0 ? C::nJ0 : seg == 3 ? C::nJ3 : C::nJ1;
+        const int I = seg == 0 ? C::I0 : seg == 3 ? C::I3 : C::I1;
+        const int J = seg == 0 ? C::J0 : seg == 3 ? C::J3 : C::J1;
+        const int hb = seg == 0 ? y.hx : seg == 3 ? y.hz + L * BP : y.hz;
+        const int db = seg == 0 ? y.dm : seg == 1 ? y.dx : seg == 2 ? y.dp : y.q;
+        const int ti = loc / nJ, tj = loc - ti * nJ;
+        const int i0 = ti * TI, j0 = tj * TJ;
+        const float* hp[TI]; const float* dq[TJ];
+#pragma unroll
+        for (int ii = 0; ii < TI; ++ii) hp[ii] = sm + hb + min(i0 + ii, I - 1) * BP;
+#pragma unroll
+        for (int jj = 0; jj < TJ; ++jj) dq[jj] = sm + db + min(j0 + jj, J - 1) * BP;
+        float acc[TI][TJ];
+#pragma unroll
+        for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < TJ; ++jj) acc[ii][jj] = 0.f;
+        for (int g4 = ks; g4 < NG; g4 += KS) {
+          float4 hv[TI], dv[TJ];
+#pragma unroll
+          for (int ii = 0; ii < TI; ++ii) hv[ii] = *reinterpret_cast<const float4*>(hp[ii] + 4 * g4);
+#pragma unroll
+          for (int jj = 0; jj < TJ; ++jj) dv[jj] = *reinterpret_cast<const float4*>(dq[jj] + 4 * g4);
+#pragma unroll
+          for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < TJ; ++jj) {
+              float a = acc[ii][jj];
+              a = fmaf(hv[ii].x, dv[jj].x, a); a = fmaf(hv[ii].y, dv[jj].y, a);
+              a = fmaf(hv[ii].z, dv[jj].z, a); a = fmaf(hv[ii].w, dv[jj].w, a);
+              acc[ii][jj] = a;
+            }
+        }
+        // split-K reduction over the KS adjacent lanes of this tile
+#pragma unroll
+        for (int off = 1; off < KS; off <<= 1)
+#pragma unroll
+          for (int ii = 0; ii < TI; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < TJ; ++jj) acc[ii][jj] += __shfl_xor_sync(0xffffffffu, acc[ii][jj], off);
+        // each lane of the group updates the tile elements e = r*KS + ks
+#pragma unroll
+        for (int r = 0; r < C::EPL; ++r) {
+          const int el = r * KS + ks;
+          float g = 0.f;
+#pragma unroll
+          for (int q = 0; q < TI * TJ; ++q) g = (el == q) ? acc[q / TJ][q % TJ] : g;
+          const int i = i0 + el / TJ, j = j0 + el % TJ;
+          if (valid && el < TI * TJ && i < I && j < J) {
+            if (seg == 3) {          // d loss / d epsilon_p[j]
+              g = g * 0.5f * sm[y.sl + j] - 0.5f * (1.f - sm[y.el + j]);
+              const float lv = adam(C::oLv + j, g);
+              const float elv = expf(lv);
+              sm[y.sl + j] = expf(0.5f * lv); sm[y.el + j] = elv;
+              sm[y.kt + (slot ^ 1) * LP + j] = 1.f + lv - elv;
+            } else {
+              const int IW = seg == 0 ? DR : L;                       // row IW is the bias row
+              const int ldp = seg == 0 ? LP : DP;
+              const int oW = seg == 0 ? C::oWe : seg == 1 ? C::oWd : C::oWs;
+              const int oB = seg == 0 ? C::oBe : seg == 1 ? C::oBd : C::oBs;
+              adam(i < IW ? oW + i * ldp + j : oB + j, g);
+            }
+          }
+        }
+      }
     }
     // no barrier here: phase A of the next step touches only z / gn / keys, which phase C
-    // does not read; the A->B barrier orders these parameter writes before the next reads.
+    // does not read; the A->B barrier orders the parameter writes before the next reads.
   }
   __syncthreads();
   // ---- store state
@@ -446,35 +499,45 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
   }
 }
 
-// (id, D, L, DR, SIG, KIND, G): every single-Dense shape of the two sweeps, plus one
-// sphere shape without hidden layers (generator coverage).
-#define VAE_SMALL_SHAPES(X)                                   \
-  X(0, 12, 20, 3, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(1, 20, 20, 3, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(2, 12, 20, 6, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(3, 20, 20, 6, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(4, 12, 20, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(5, 20, 10, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3)         \
-  X(6, 20, 10, 12, false, VAE_DATA_LINEAR_GAUSSIAN, 3)        \
-  X(7, 7, 6, 4, true, VAE_DATA_SIGMOID, 3)                    \
-  X(8, 17, 8, 4, true, VAE_DATA_SIGMOID, 3)                   \
-  X(9, 22, 16, 6, true, VAE_DATA_SIGMOID, 5)                  \
-  X(10, 11, 10, 6, true, VAE_DATA_SIGMOID, 5)                 \
-  X(11, 15, 13, 8, true, VAE_DATA_SIGMOID, 7)                 \
-  X(12, 28, 24, 8, true, VAE_DATA_SIGMOID, 7)                 \
-  X(13, 6, 6, 3, false, VAE_DATA_SPHERE, 3)
+// (id, D, L, DR, SIG, KIND, G, TI, TJ): every single-Dense shape of the two sweeps, plus one
+// sphere shape without hidden layers (generator coverage).  TI x TJ = gradient tile.
+#define VAE_SMALL_SHAPES(X)                                         \
+  X(0, 12, 20, 3, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(1, 20, 20, 3, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(2, 12, 20, 6, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(3, 20, 20, 6, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(4, 12, 20, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(5, 20, 10, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
+  X(6, 20, 10, 12, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)        \
+  X(7, 7, 6, 4, true, VAE_DATA_SIGMOID, 3, 2, 2)                    \
+  X(8, 17, 8, 4, true, VAE_DATA_SIGMOID, 3, 2, 4)                   \
+  X(9, 22, 16, 6, true, VAE_DATA_SIGMOID, 5, 4, 4)                  \
+  X(10, 11, 10, 6, true, VAE_DATA_SIGMOID, 5, 2, 4)                 \
+  X(11, 15, 13, 8, true, VAE_DATA_SIGMOID, 7, 4, 4)                 \
+  X(12, 28, 24, 8, true, VAE_DATA_SIGMOID, 7, 4, 4)                 \
+  X(13, 6, 6, 3, false, VAE_DATA_SPHERE, 3, 2, 2)
 
+// heterogeneous packs: one launch, dispatch on the job's shape
 __global__ void __launch_bounds__(kT)
 fused_small_kernel(const FusedJobDev* __restrict__ jobs, int64_t n_steps) {
   extern __shared__ __align__(16) float sm[];
   const FusedJobDev job = jobs[blockIdx.x];
   switch (job.shape_id) {
-#define X(id, D, L, DR, SIG, KIND, G) \
-    case id: fused_small_run<SmallCfg<D, L, DR, SIG, KIND, G>>(job, n_steps, sm); break;
+#define X(id, D, L, DR, SIG, KIND, G, TI, TJ) \
+    case id: fused_small_run<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>(job, n_steps, sm); break;
     VAE_SMALL_SHAPES(X)
 #undef X
     default: break;
   }
+}
+
+// homogeneous packs: a kernel per shape, so registers / occupancy are the shape's own
+template <class C>
+__global__ void __launch_bounds__(kT, C::MINB)
+fused_small_kernel_one(const FusedJobDev* __restrict__ jobs, int64_t n_steps) {
+  extern __shared__ __align__(16) float sm[];
+  const FusedJobDev job = jobs[blockIdx.x];
+  fused_small_run<C>(job, n_steps, sm);
 }
 
 // Returns the shape id (>= 0) or -1; *smem_floats receives the CTA's shared memory need.
@@ -488,9 +551,9 @@ static int small_shape_of(const VaeTrainJob* j, int* smem_floats) {
   if ((d.sig_decoder != 0) != (g.kind == VAE_DATA_SIGMOID)) return -1;
   const int dr = g.dim + (g.kind == VAE_DATA_SIGMOID ? 1 : 0);
   const int gg = g.kind == VAE_DATA_LINEAR_GAUSSIAN ? g.intrinsic_dim : g.dim;
-#define X(id, D, L, DR, SIG, KIND, G)                                                        \
+#define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                \
   if (d.data_dim == D && d.latent_dim == L && dr == DR && g.kind == KIND && gg == G) {       \
-    *smem_floats = SmallCfg<D, L, DR, SIG, KIND, G>::layout(d.batch).total;                  \
+    *smem_floats = SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>::layout(d.batch).total;          \
     return id;                                                                               \
   }
   VAE_SMALL_SHAPES(X)
@@ -500,9 +563,60 @@ static int small_shape_of(const VaeTrainJob* j, int* smem_floats) {
 
 constexpr int kMaxSmem = 227 * 1024;
 
+static int launch_small(int shape_id, bool homogeneous, int n_jobs, size_t smem, const FusedJobDev* d_jobs,
+                        int64_t n_steps, cudaStream_t s) {
+  if (homogeneous) {
+    switch (shape_id) {
+#define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                              \
+      case id: {                                                                                           \
+        auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>;                         \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        k<<<n_jobs, kT, smem, s>>>(d_jobs, n_steps);                                                       \
+        break;                                                                                             \
+      }
+      VAE_SMALL_SHAPES(X)
+#undef X
+      default: set_error("bad shape id %d", shape_id); return VAE_ERR_INVALID;
+    }
+  } else {
+    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    fused_small_kernel<<<n_jobs, kT, smem, s>>>(d_jobs, n_steps);
+  }
+  VAE_LAUNCH_OK("fused_small_kernel");
+  return 0;
+}
+
+static int occupancy_small(int shape_id, size_t smem, int* out) {
+  switch (shape_id) {
+#define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                              \
+    case id: {                                                                                           \
+      auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>;                         \
+      VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+      VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+      VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, kT, smem));                      \
+      break;                                                                                             \
+    }
+    VAE_SMALL_SHAPES(X)
+#undef X
+    default: set_error("bad shape id %d", shape_id); return VAE_ERR_INVALID;
+  }
+  return 0;
+}
+
 }  // namespace vae
 
 extern "C" {
+
+int vae_train_fused_ctas_per_sm(const VaeTrainJob* job) {
+  VAE_REQUIRE(job, "vae_train_fused_ctas_per_sm: job is NULL");
+  int fl = 0, out = 0;
+  const int id = vae::small_shape_of(job, &fl);
+  if (id < 0 || (size_t)fl * 4 > (size_t)vae::kMaxSmem) return 0;
+  const int rc = vae::occupancy_small(id, (size_t)fl * sizeof(float), &out);
+  return rc ? rc : out;
+}
 
 int vae_train_fused_supported(const VaeTrainJob* job) {
   if (!job) return 0;
@@ -528,6 +642,7 @@ int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, vo
   vae::FusedJobDev* host = (vae::FusedJobDev*)malloc((size_t)n_jobs * sizeof(vae::FusedJobDev));
   VAE_REQUIRE(host, "vae_train_fused: out of host memory");
   int max_fl = 0;
+  bool homogeneous = true;
   for (int i = 0; i < n_jobs; ++i) {
     const VaeTrainJob& j = jobs[i];
     int fl = 0;
@@ -548,21 +663,20 @@ int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, vo
     vae::FusedJobDev& o = host[i];
     o.params = j.params; o.adam_m = j.adam_m; o.adam_v = j.adam_v; o.step = j.step;
     o.model_key = j.model_key; o.dataset_key = j.dataset_key; o.A = j.A; o.loss_out = j.loss_out;
-    o.batch = j.desc.batch; o.tunable = j.desc.tunable_decoder_var; o.shape_id = id; o.pad_ = 0; o.dbg = (float*)j.workspace;
+    o.batch = j.desc.batch; o.tunable = j.desc.tunable_decoder_var; o.shape_id = id; o.pad_ = 0;
     const vae::AdamHyper hp = vae::make_adam_hyper(&j.desc);
     o.eps0 = (float)j.desc.epsilon0; o.lr = hp.lr; o.b1 = hp.b1; o.b2 = hp.b2; o.omb1 = hp.omb1; o.omb2 = hp.omb2;
     o.adam_eps = hp.eps;
+    if (id != host[0].shape_id || o.batch != host[0].batch) homogeneous = false;
   }
   // pageable-source async copies are staged before the call returns, so `host` may be freed
   cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * sizeof(vae::FusedJobDev),
                                   cudaMemcpyHostToDevice, s);
+  const int shape0 = host[0].shape_id;
   free(host);
   VAE_CUDA_OK(e);
-  const size_t smem = (size_t)max_fl * sizeof(float);
-  VAE_CUDA_OK(cudaFuncSetAttribute(vae::fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  vae::fused_small_kernel<<<n_jobs, vae::kT, smem, s>>>((const vae::FusedJobDev*)d_scratch, n_steps);
-  VAE_LAUNCH_OK("fused_small_kernel");
-  return 0;
+  return vae::launch_small(shape0, homogeneous, n_jobs, (size_t)max_fl * sizeof(float),
+                           (const vae::FusedJobDev*)d_scratch, n_steps, s);
 }
 
 }  // extern "C"

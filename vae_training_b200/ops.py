@@ -190,6 +190,13 @@ def fused_supported(job: VaeTrainJob) -> int:
     return int(_lib.load().vae_train_fused_supported(C.byref(job)))
 
 
+def fused_ctas_per_sm(job: VaeTrainJob) -> int:
+    n = int(_lib.load().vae_train_fused_ctas_per_sm(C.byref(job)))
+    if n < 0:
+        check(n, "vae_train_fused_ctas_per_sm")
+    return n
+
+
 def train_fused(jobs: Sequence[VaeTrainJob], n_steps: int, scratch: torch.Tensor):
     """One persistent launch: n_steps consecutive hot-loop iterations (model.py:221-222)
     for every job."""
