@@ -101,6 +101,13 @@ int vae_random_normal(const uint32_t* d_key, float* d_out, int64_t n, void* stre
 int vae_random_normal_rows(const uint32_t* d_key, float* d_out, int64_t rows, int64_t cols,
                            int64_t row_begin, int64_t row_end, void* stream);
 
+/* Data-parallel shard of random.normal(key, (rows, cols)), rows even: global rows [lo, hi)
+ * (lo <= hi <= rows/2) followed by their threefry partners [rows/2 + lo, rows/2 + hi), written
+ * densely as (2*(hi-lo), cols).  Row b and row b + rows/2 come out of the same threefry
+ * blocks, so a shard made of such pairs computes no block it does not use. */
+int vae_random_normal_pairs(const uint32_t* d_key, float* d_out, int64_t rows, int64_t cols,
+                            int64_t lo, int64_t hi, void* stream);
+
 /* -------------------------------------------------------------------- datasets
  * Replaces <Dataset>.get_batch(size) given the already-split batch key
  * (datasets.py:75-84, 183-195, 240-249).  d_A: device generator matrix
@@ -108,6 +115,9 @@ int vae_random_normal_rows(const uint32_t* d_key, float* d_out, int64_t rows, in
  * d_out: device (size, vae_data_width) float32. */
 int vae_dataset_batch(const VaeDataDesc* d, const uint32_t* d_key, const float* d_A,
                       int32_t size, float* d_out, void* stream);
+/* The same rows/partners shard of <Dataset>.get_batch(size): (2*(hi-lo), width). */
+int vae_dataset_batch_pairs(const VaeDataDesc* d, const uint32_t* d_key, const float* d_A,
+                            int32_t size, int32_t lo, int32_t hi, float* d_out, void* stream);
 /* Replaces <Dataset>.score_batch(batch) (datasets.py:67-73, 201-206, 255-261).
  * d_scores: device float[2] = {first, second} statistic in the reference's dict order
  * (second is 0 for linear_gaussian). */

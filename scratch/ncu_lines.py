@@ -50,22 +50,28 @@ for ln, (s, e) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
 # ---- region summary
 reg = collections.defaultdict(lambda: [0, 0])
 def region(ln):
+    import re as _re
     if ln is None: return "none"
     f, n = ln
-    if f == "common.cuh":
-        if n <= 57: return "threefry"
-        if n <= 110: return "log1p"
-        if n <= 135: return "erfinv+normal"
-        if n <= 157: return "det_exp/sigmoid"
-        return "warp_sum"
-    if f == "fused_small.cu":
-        if n < 197: return "init"
-        if n < 229: return "phaseA-loop/idx"
-        if n < 357: return "phaseB"
-        if n < 440: return "phaseC"
-        return "store"
+    def marks(path, pats):
+        out = []
+        for k, l in enumerate(open(path).read().splitlines(), 1):
+            for name, pat in pats:
+                if pat in l: out.append((k, name))
+        return sorted(out)
+    global _mk
+    try: _mk
+    except NameError:
+        _mk = {"common.cuh": marks("/root/repo/vae_training_b200/csrc/common.cuh", [("threefry", "void threefry2x32("), ("threefry", "void threefry2x32_x2("), ("split", "void split2("), ("log1p", "float neg_log1p_neg("), ("erfinv", "float erf_inv_f32("), ("normal", "float normal_from_bits("), ("normal_fast", "float normal_from_bits_fast("), ("det_exp", "float det_expf("), ("warp_sum", "float warp_sum("), ("hosthelpers", "struct AdamHyper")]),
+               "fused_small.cu": marks("/root/repo/vae_training_b200/csrc/fused_small.cu", [("init", "---- load state"), ("phaseA", "phase A: random"), ("phaseB", "phase B: one thread"), ("phaseC", "phase C: gradient"), ("store", "---- store state"), ("pre", "namespace vae {")])}
+    if f in _mk:
+        r = "pre"
+        for k, name in _mk[f]:
+            if n >= k: r = name
+        return f.split(".")[0][:6] + ":" + r
     return f
+NCTA = int(__import__("os").environ.get("NCTA", "888")); NSTEP = int(__import__("os").environ.get("NSTEP", "2000"))
 for ln, (s, e) in by_line.items():
     r = region(ln); reg[r][0] += s; reg[r][1] += e
 for r, (s, e) in sorted(reg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{r:22s} samples {100*s/tot_s:5.1f}%  instr {100*e/tot_e:5.1f}%  warp-instr/CTA-step {e/ (444*2000):8.1f}")
+    print(f"{r:22s} samples {100*s/tot_s:5.1f}%  instr {100*e/tot_e:5.1f}%  warp-instr/CTA-step {e/(NCTA*NSTEP):8.1f}")

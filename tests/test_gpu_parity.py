@@ -444,3 +444,68 @@ def test_fused_unsupported_shape_is_refused(ops, lib):
     assert ops.fused_supported(job) == 0
     with pytest.raises(lib.VaeB200Error):
         ops.train_fused([job], 4, ops.fused_scratch(1))
+
+
+# ------------------------------------------------------------ data-parallel sharding
+
+@pytest.mark.parametrize("rows,cols,lo,hi", [(100, 13, 0, 50), (100, 13, 12, 31), (64, 1040, 8, 16), (2, 5, 0, 1), (8, 3, 2, 2)])
+def test_normal_pairs_bit_exact(ops, rows, cols, lo, hi):
+    from vae_training_b200 import dp
+    key = jr.PRNGKey(17)
+    got = ops.random_normal_pairs(ops.key_tensor(key), rows, cols, lo, hi).cpu().numpy()
+    ref = jr.normal(key, (rows, cols))[dp.shard_row_indices(rows, lo, hi)]
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,dd,pd", [("sphere", 5, 3), ("linear_gaussian", 6, 2), ("sigmoid", 3, 3)])
+def test_dataset_pairs_bit_exact(ops, lib, name, dd, pd):
+    from vae_training_b200 import dp
+    size = 64
+    ds = ods.make_dataset(name, 24, dd, pd)
+    key = ds.key.copy()
+    ref = ds.get_batch(size)
+    bkey, _ = jr.dataset_chain_next(key)
+    A = dev(ds.A.astype(np.float32)) if ds.A is not None else None
+    for lo, hi in ((0, 32), (5, 19), (31, 32)):
+        got = ops.dataset_batch_pairs(lib.make_data_desc(name, dd, pd), ops.key_tensor(bkey), A, size, lo, hi).cpu().numpy()
+        np.testing.assert_array_equal(got.view(np.uint32), ref[dp.shard_row_indices(size, lo, hi)].view(np.uint32))
+
+
+def test_data_parallel_emulated_ranks_match_single(ops, lib):
+    """Three emulated ranks (one GPU, sequential): their scaled gradients add up to the
+    single-rank gradient, and a world-1 DataParallelVAE follows the oracle loop."""
+    from vae_training_b200 import dp
+    from vae_training_b200.packed import RunSpec
+    spec = RunSpec("sphere", 5, 3, 4, [32, 24], [24, 32], batch_size=60, learning_rate=1e-4, epsilon=-2.0,
+                   tunable_decoder_var=True)
+    d = vs.VaeDesc(60, 8, 4, [32, 24], [24, 32], epsilon0=-2.0, lr=1e-4)
+    flat = vs.init_params(d, 2)
+    mk, dk = jr.PRNGKey(11), jr.PRNGKey(12)
+    single = dp.DataParallelVAE(spec, flat, mk, dk, rank=0, world=1)
+    x, z = single.draw()
+    ws = ops.Workspace()
+    full = torch.zeros(d.n_params + 1, device="cuda")
+    ops.loss_and_grad(single.desc, single.params, x, z, 60, 60, full[d.n_params:], full[:d.n_params], ws)
+    acc = torch.zeros_like(full)
+    for r in range(3):
+        m = dp.DataParallelVAE(spec, flat, mk, dk, rank=r, world=3)
+        xr, zr = m.draw()
+        idx = dp.shard_row_indices(60, m.lo, m.hi)
+        assert torch.equal(xr, x[idx]) and torch.equal(zr, z[idx])
+        g = torch.zeros_like(full)
+        ops.loss_and_grad(m.desc, m.params, xr, zr, m.rows, 60, g[d.n_params:], g[:d.n_params], ws)
+        acc += g
+    assert relerr(acc.cpu().numpy(), full.cpu().numpy()) <= 2e-6
+    # world-1 DP == oracle loop
+    ods_ = ods.SphereDataset(0, 5, 3)
+    ods_.key = dk.copy()
+    tr = otr.OracleTrainer(d, ods_, flat, dtype=np.float64)
+    tr.key = mk.copy()
+    tr.started = True
+    model = dp.DataParallelVAE(spec, flat, mk, dk, rank=0, world=1)
+    got = torch.cat([model.train_step().clone() for _ in range(10)]).cpu().numpy()
+    tr.train(10 ** 9, 0, 10, events=False)
+    ref = np.array(tr.train_losses)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
+    np.testing.assert_array_equal(model.key.cpu().numpy(), tr.key)
+    np.testing.assert_array_equal(model.dkey.cpu().numpy(), ods_.key)

@@ -54,6 +54,8 @@ _PROTOTYPES = {
     "vae_random_bits": (C.c_int, [_P, _P, C.c_int64, _P]),
     "vae_random_normal": (C.c_int, [_P, _P, C.c_int64, _P]),
     "vae_random_normal_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "vae_random_normal_pairs": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "vae_dataset_batch_pairs": (C.c_int, [C.POINTER(VaeDataDesc), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vae_dataset_batch": (C.c_int, [C.POINTER(VaeDataDesc), _P, _P, C.c_int32, _P, _P]),
     "vae_dataset_score": (C.c_int, [C.POINTER(VaeDataDesc), _P, _P, C.c_int32, _P, _P]),
     "vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_int32]),

@@ -58,6 +58,18 @@ __global__ void dataset_batch_kernel(VaeDataDesc d, const uint32_t* __restrict__
   dataset_row(d, key[0], key[1], A, row, size, out + (int64_t)row * width);
 }
 
+// Data-parallel shard (see normal_pairs_kernel): local row i < n_lo is global row lo + i,
+// local row n_lo + i is its partner size/2 + lo + i.
+__global__ void dataset_pairs_kernel(VaeDataDesc d, const uint32_t* __restrict__ key,
+                                     const float* __restrict__ A, int size, int lo, int n_lo,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_lo) return;
+  const int row = i < n_lo ? lo + i : size / 2 + lo + (i - n_lo);
+  const int width = d.dim + d.padding_dim + (d.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  dataset_row(d, key[0], key[1], A, row, size, out + (int64_t)i * width);
+}
+
 // One block; double accumulation (statistics only, tolerance-level parity).
 __global__ void dataset_score_kernel(VaeDataDesc d, const float* __restrict__ A,
                                      const float* __restrict__ batch, int size, float* __restrict__ scores) {
@@ -127,6 +139,23 @@ int vae_dataset_batch(const VaeDataDesc* d, const uint32_t* d_key, const float* 
   VAE_REQUIRE((int64_t)size * vae_data_normals_per_row(d) < (1ll << 32), "vae_dataset_batch: too many draws");
   vae::dataset_batch_kernel<<<(size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d, d_key, d_A, size, d_out);
   VAE_LAUNCH_OK("dataset_batch_kernel");
+  return 0;
+}
+
+int vae_dataset_batch_pairs(const VaeDataDesc* d, const uint32_t* d_key, const float* d_A,
+                            int32_t size, int32_t lo, int32_t hi, float* d_out, void* stream) {
+  int rc = vae::check_data_desc(d);
+  if (rc) return rc;
+  VAE_REQUIRE(d_key && size >= 0 && size % 2 == 0, "vae_dataset_batch_pairs: size must be even and >= 0");
+  VAE_REQUIRE(lo >= 0 && lo <= hi && hi <= size / 2, "vae_dataset_batch_pairs: bad row range");
+  VAE_REQUIRE(d->kind == VAE_DATA_SPHERE || d_A, "vae_dataset_batch_pairs: generator matrix A is NULL");
+  const int n_lo = hi - lo;
+  if (n_lo == 0) return 0;
+  VAE_REQUIRE(d_out, "vae_dataset_batch_pairs: d_out is NULL");
+  VAE_REQUIRE((int64_t)size * vae_data_normals_per_row(d) < (1ll << 32), "vae_dataset_batch_pairs: too many draws");
+  vae::dataset_pairs_kernel<<<(2 * n_lo + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d, d_key, d_A, size, lo,
+                                                                                      n_lo, d_out);
+  VAE_LAUNCH_OK("dataset_pairs_kernel");
   return 0;
 }
 

@@ -80,7 +80,7 @@ struct SmallCfg {
   static constexpr int EPL = cdiv(TI * TJ, KS);          // tile elements updated per lane
   // CTAs per SM the per-shape kernel is compiled for (register cap), from the shared-memory
   // footprint at the reference batch size 100
-  static constexpr int SMEM100 = 4 * (3 * PP + 4 * LP + 32 + up4(AN + 1) + 8 + up4(100 * SZ) + up4(100 * SG) +
+  static constexpr int SMEM100 = 4 * (3 * PP + 4 * LP + 40 + up4(AN + 1) + 8 + up4(100 * SZ) + up4(100 * SG) +
                                       (DR + 1 + L + 1 + 2 * L + D * NDEC) * 100) + 1024;
   static constexpr int MINB_RAW = (227 * 1024) / SMEM100;
   static constexpr int MINB = MINB_RAW < 1 ? 1 : MINB_RAW > VAE_SMALL_MAXB ? VAE_SMALL_MAXB : MINB_RAW;
@@ -94,7 +94,7 @@ struct SmallCfg {
     y.P = o; o += PP; y.M = o; o += PP; y.V = o; o += PP;
     y.sl = o; o += LP; y.el = o; o += LP;
     y.kt = o; o += 2 * LP;         // [2 slots][LP]  1 + lv - e^lv (KL term of the loss)
-    y.scal = o; o += 8;            // [2 slots][e, sd, inv_var, -]
+    y.scal = o; o += 16;           // [2 slots][e, sd, inv_var, -, 1/bc1, 1/bc2, -, -]
     y.red = o; o += 16;            // [3][4] warp partials
     y.A = o; o += up4(AN + 1);
     y.keys = o; o += 8;            // uint32 [2 slots][lat0 lat1 bat0 bat1]
@@ -131,6 +131,12 @@ struct SmallCfg {
   }
 };
 
+// sqrt.approx (1 MUFU + fix-up, exact at 0): ample for Adam's denominator
+__device__ __forceinline__ float approx_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 template <class C>
@@ -166,11 +172,16 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
   }
   if (t == 0) {
     const float e = tunable ? P[C::oEp] * job.eps0 : job.eps0;
-    for (int q = 0; q < 2; ++q) { sm[y.scal + 4 * q] = e; sm[y.scal + 4 * q + 1] = expf(0.5f * e); sm[y.scal + 4 * q + 2] = expf(-e); }
+    for (int q = 0; q < 2; ++q) { sm[y.scal + 8 * q] = e; sm[y.scal + 8 * q + 1] = expf(0.5f * e); sm[y.scal + 8 * q + 2] = expf(-e); }
   }
-  // Adam bias-correction powers (double running products of the float32 betas)
+  // Adam bias corrections 1/(1 - beta^t): thread kT-1 keeps double running products of the
+  // float32 betas and publishes the float32 factors for the NEXT step (slot parity)
   const int32_t step0 = job.step[0];
-  double b1t = pow((double)job.b1, (double)step0), b2t = pow((double)job.b2, (double)step0);
+  double b1t = 0.0, b2t = 0.0;
+  if (t == kT - 1) {
+    b1t = pow((double)job.b1, (double)step0 + 1.0); b2t = pow((double)job.b2, (double)step0 + 1.0);
+    sm[y.scal + 4] = 1.0f / (1.0f - (float)b1t); sm[y.scal + 5] = 1.0f / (1.0f - (float)b2t);
+  }
 
   // ---- key chains: lanes 0,1 own the model-side split, lanes 2,3 the dataset-side one
   uint32_t ck0 = 0, ck1 = 0;           // carried key of this lane's chain
@@ -245,7 +256,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     // ================= phase B: one thread per batch row
     float kl_acc = 0.f, r2_acc = 0.f, rz_acc = 0.f;
     {
-      const float sd = sm[y.scal + 4 * slot + 1], inv_var = sm[y.scal + 4 * slot + 2];
+      const float sd = sm[y.scal + 8 * slot + 1], inv_var = sm[y.scal + 8 * slot + 2];
       const float gscale = inv_var * invB;
       for (int b = t; b < B; b += kT) {
         const float* zr = sm + y.z + b * C::SZ;
@@ -375,9 +386,8 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     __syncthreads();
     // ================= phase C: gradient tiles + Adam
     {
-      b1t *= (double)job.b1; b2t *= (double)job.b2;
-      const float ibc1 = 1.0f / (1.0f - (float)b1t), ibc2 = 1.0f / (1.0f - (float)b2t);
-      const float e = sm[y.scal + 4 * slot], sd = sm[y.scal + 4 * slot + 1], inv_var = sm[y.scal + 4 * slot + 2];
+      const float* scs = sm + y.scal + 8 * slot;
+      const float e = scs[0], sd = scs[1], inv_var = scs[2], ibc1 = scs[4], ibc2 = scs[5];
       const float s_mu2 = (sm[y.red + 0] + sm[y.red + 1]) + (sm[y.red + 2] + sm[y.red + 3]);
       const float s_r2 = (sm[y.red + 4] + sm[y.red + 5]) + (sm[y.red + 6] + sm[y.red + 7]);
       const float s_rz = (sm[y.red + 8] + sm[y.red + 9]) + (sm[y.red + 10] + sm[y.red + 11]);
@@ -386,7 +396,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
         const float m = job.b1 * M[poff] + job.omb1 * g;
         const float v = job.b2 * V[poff] + job.omb2 * g * g;
         M[poff] = m; V[poff] = v;
-        const float p = P[poff] - job.lr * (m * ibc1) / (sqrtf(v * ibc2) + job.adam_eps);
+        const float p = P[poff] - __fdividef(job.lr * (m * ibc1), approx_sqrt(v * ibc2) + job.adam_eps);
         P[poff] = p;
         return p;
       };
@@ -397,11 +407,13 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
         const float dkl = (-0.5f * klc * fB + 0.5f * s_mu2) * invB;
         const float mse = (0.5f * inv_var * s_r2 + 0.5f * (1.8378770664093453f + e) * fB * (float)D) * invB;
         job.loss_out[s] = dkl + mse;
+        float* scn = sm + y.scal + 8 * (slot ^ 1);
+        b1t *= (double)job.b1; b2t *= (double)job.b2;
+        scn[4] = 1.0f / (1.0f - (float)b1t); scn[5] = 1.0f / (1.0f - (float)b2t);
         if (tunable) {     // d loss / d epsilon (param) = eps0 * dL/de
           const float g = job.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
           const float e2 = adam(C::oEp, g) * job.eps0;
-          float* sc = sm + y.scal + 4 * (slot ^ 1);
-          sc[0] = e2; sc[1] = expf(0.5f * e2); sc[2] = expf(-e2);
+          scn[0] = e2; scn[1] = expf(0.5f * e2); scn[2] = expf(-e2);
         }
       }
 #pragma unroll 1

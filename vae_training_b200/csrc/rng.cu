@@ -46,6 +46,23 @@ __global__ void normal_rows_kernel(const uint32_t* __restrict__ key, float* __re
     out[t] = normal_from_bits(random_bits_at(k0, k1, (uint32_t)(first + t), (uint32_t)n));
 }
 
+// Data-parallel shard of normal(key, (rows, cols)), rows even: the shard owns global rows
+// [lo, hi) and their threefry partners [lo + rows/2, hi + rows/2) (block j of the flat
+// array yields elements j and j + rows*cols/2, i.e. the same column of row b and of row
+// b + rows/2).  Output: (2*(hi-lo), cols), first the low rows then the partner rows.  Every
+// threefry block computed is fully used.
+__global__ void normal_pairs_kernel(const uint32_t* __restrict__ key, float* __restrict__ out,
+                                    int64_t half, int64_t first, int64_t count) {
+  const uint32_t k0 = key[0], k1 = key[1];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    uint32_t x0 = (uint32_t)(first + t), x1 = (uint32_t)(first + t + half);
+    threefry2x32(k0, k1, x0, x1);
+    out[t] = normal_from_bits(x0);
+    out[t + count] = normal_from_bits(x1);
+  }
+}
+
 static inline int grid_for(int64_t work, int threads) {
   int64_t b = (work + threads - 1) / threads;
   const int64_t cap = 148 * 16;   // multiples of the SM count; grid-stride beyond that
@@ -93,6 +110,20 @@ int vae_random_normal_rows(const uint32_t* d_key, float* d_out, int64_t rows, in
   vae::normal_rows_kernel<<<vae::grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
       d_key, d_out, rows * cols, row_begin * cols, count);
   VAE_LAUNCH_OK("normal_rows_kernel");
+  return 0;
+}
+
+int vae_random_normal_pairs(const uint32_t* d_key, float* d_out, int64_t rows, int64_t cols,
+                            int64_t lo, int64_t hi, void* stream) {
+  VAE_REQUIRE(d_key && rows >= 0 && cols >= 0 && rows * cols < (1ll << 32), "vae_random_normal_pairs: bad shape");
+  VAE_REQUIRE(rows % 2 == 0, "vae_random_normal_pairs: rows must be even (got %lld)", (long long)rows);
+  VAE_REQUIRE(lo >= 0 && lo <= hi && hi <= rows / 2, "vae_random_normal_pairs: bad row range");
+  const int64_t count = (hi - lo) * cols;
+  if (count == 0) return 0;
+  VAE_REQUIRE(d_out, "vae_random_normal_pairs: d_out is NULL");
+  vae::normal_pairs_kernel<<<vae::grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_key, d_out, rows * cols / 2, lo * cols, count);
+  VAE_LAUNCH_OK("normal_pairs_kernel");
   return 0;
 }
 

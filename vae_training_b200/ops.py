@@ -76,7 +76,25 @@ def random_normal_rows(key: torch.Tensor, rows: int, cols: int, row_begin: int, 
     return out
 
 
+def random_normal_pairs(key: torch.Tensor, rows: int, cols: int, lo: int, hi: int) -> torch.Tensor:
+    """Rows [lo, hi) and partners [rows/2 + lo, rows/2 + hi) of random.normal(key, (rows, cols))."""
+    out = torch.empty((2 * (hi - lo), cols), dtype=torch.float32, device=key.device)
+    check(_lib.load().vae_random_normal_pairs(_ptr(key, torch.uint32, "key"), _ptr(out), rows, cols, lo, hi,
+                                               _stream()), "vae_random_normal_pairs")
+    return out
+
+
 # ------------------------------------------------------------------------ datasets
+
+def dataset_batch_pairs(data: VaeDataDesc, key: torch.Tensor, A: Optional[torch.Tensor], size: int, lo: int,
+                        hi: int) -> torch.Tensor:
+    lib = _lib.load()
+    width = lib.vae_data_width(C.byref(data))
+    out = torch.empty((2 * (hi - lo), width), dtype=torch.float32, device=key.device)
+    check(lib.vae_dataset_batch_pairs(C.byref(data), _ptr(key, torch.uint32, "key"), _ptr(A, torch.float32, "A"),
+                                      size, lo, hi, _ptr(out), _stream()), "vae_dataset_batch_pairs")
+    return out
+
 
 def dataset_batch(data: VaeDataDesc, key: torch.Tensor, A: Optional[torch.Tensor], size: int) -> torch.Tensor:
     lib = _lib.load()
