@@ -476,8 +476,8 @@ def test_data_parallel_emulated_ranks_match_single(ops, lib):
     single-rank gradient, and a world-1 DataParallelVAE follows the oracle loop."""
     from vae_training_b200 import dp
     from vae_training_b200.packed import RunSpec
-    spec = RunSpec("sphere", 5, 3, 4, [32, 24], [24, 32], batch_size=60, learning_rate=1e-4, epsilon=-2.0,
-                   tunable_decoder_var=True)
+    spec = RunSpec("sphere", 5, 3, 4, encoder_layer_sizes=[32, 24], layer_sizes=[24, 32], batch_size=60,
+                   learning_rate=1e-4, epsilon=-2.0, tunable_decoder_var=True)
     d = vs.VaeDesc(60, 8, 4, [32, 24], [24, 32], epsilon0=-2.0, lr=1e-4)
     flat = vs.init_params(d, 2)
     mk, dk = jr.PRNGKey(11), jr.PRNGKey(12)
