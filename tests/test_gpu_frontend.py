@@ -55,11 +55,11 @@ def compare(m, tr, ods_, N):
 @pytest.mark.parametrize("name,dd,pd,L,hidden", [("sigmoid", 3, 3, 6, ""), ("linear_gaussian", 3, 9, 20, ""),
                                                  ("sphere", 3, 3, 6, "24|16")])
 def test_train_schedule_matches_oracle(name, dd, pd, L, hidden):
-    """model.py:207-222 end to end (fused path for the single-Dense shapes, per-op path for
-    the hidden-layer one): interleaved train/eval losses, learned variances, stats, key chains."""
+    """model.py:207-222 end to end (single-CTA fused kernel for the single-Dense shapes, cluster
+    kernel for the hidden-layer one): interleaved train/eval losses, learned variances, stats, key chains."""
     N = 30
     m, tr, ods_ = build_pair(name, dd, pd, L, hidden, N, seed=2 if name == "linear_gaussian" else 69)
-    assert m.fused == (hidden == "")
+    assert m.fused_class == (1 if hidden == "" else 2)
     m.train_distribution(save=False)
     tr.train(N)
     compare(m, tr, ods_, N)

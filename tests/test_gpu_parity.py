@@ -509,3 +509,103 @@ def test_data_parallel_emulated_ranks_match_single(ops, lib):
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
     np.testing.assert_array_equal(model.key.cpu().numpy(), tr.key)
     np.testing.assert_array_equal(model.dkey.cpu().numpy(), ods_.key)
+
+
+# ------------------------------------------------ fused cluster kernel (hidden-layer models)
+
+MLP_CASES = [
+    # (dataset, dd, pd, L, enc_hidden, dec_hidden, batch, seed)
+    ("sphere", 3, 3, 6, [200, 200, 200], [200, 200, 200], 100, 69),
+    ("sphere", 3, 13, 8, [200, 200, 200], [200, 200, 200], 100, 24),
+    ("sphere", 5, 16, 16, [200, 200, 200], [200, 200, 200], 100, 48),
+    ("sphere", 5, 5, 10, [200, 200, 200], [200, 200, 200], 100, 69),
+    ("sphere", 7, 7, 13, [200, 200, 200], [200, 200, 200], 100, 24),
+    ("sphere", 4, 1, 3, [17], [9, 33], 37, 5),
+    ("linear_gaussian", 6, 2, 5, [64, 48], [48], 64, 2),
+]
+
+
+def mlp_setup(ops, lib, case, n_steps):
+    name, dd, pd, L, eh, dh, batch, seed = case
+    ds = ods.make_dataset(name, seed, dd, pd)
+    d = vs.VaeDesc(batch, ds.ndim, L, eh, dh, epsilon0=-3.0, lr=1e-4)
+    flat = vs.init_params(d, seed=0)
+    tr = otr.OracleTrainer(d, ds, flat, dtype=np.float64)
+    tr.begin()
+    st = dict(
+        P=dev(flat), M=torch.zeros(d.n_params, device="cuda"), V=torch.zeros(d.n_params, device="cuda"),
+        step=torch.zeros(1, dtype=torch.int32, device="cuda"),
+        mk=ops.key_tensor(tr.key), dk=ops.key_tensor(ds.key),
+        A=dev(ds.A.astype(np.float32)) if ds.A is not None else None,
+        loss=torch.zeros(max(n_steps, 1), device="cuda"),
+    )
+    mk_job = lambda ws: ops.make_job(odesc_to_c(lib, d), lib.make_data_desc(name, dd, pd), st["P"], st["M"], st["V"],
+                                     st["step"], st["mk"], st["dk"], st["A"], st["loss"], workspace=ws)
+    job = mk_job(None)
+    assert ops.fused_supported(job) == 2
+    st["ws"] = ops.fused_workspace(job)
+    assert st["ws"] is not None
+    return d, ds, tr, st, mk_job(st["ws"])
+
+
+@pytest.mark.parametrize("case", MLP_CASES, ids=lambda c: f"{c[0]}_dd{c[1]}_pd{c[2]}_L{c[3]}_h{len(c[4])}{len(c[5])}")
+def test_fused_cluster_vs_oracle_loop(ops, lib, case):
+    """The cluster kernel's n steps == n iterations of model.py:221-222 in the oracle."""
+    n = 12
+    d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), tr.key)
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), ds.key)
+    assert int(st["step"]) == n
+    got = st["loss"].cpu().numpy().astype(np.float64)
+    ref = np.array(tr.train_losses, np.float64)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
+    assert_params_close(st["P"].cpu().numpy(), tr.params, n, d.lr, frac=0.95)
+    assert relerr(st["M"].cpu().numpy(), tr.m) <= 1e-4
+    assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
+
+
+def test_fused_cluster_first_step_gradient_exact_path(ops, lib):
+    """One step with adam_eps = 1 (well-conditioned): every parameter within 1e-3 * lr."""
+    import dataclasses
+    case = MLP_CASES[2]
+    name, dd, pd, L, eh, dh, batch, seed = case
+    ds = ods.make_dataset(name, seed, dd, pd)
+    d = vs.VaeDesc(batch, ds.ndim, L, eh, dh, epsilon0=-3.0, lr=1e-4, adam_eps=1.0)
+    flat = vs.init_params(d, seed=0)
+    tr = otr.OracleTrainer(d, ds, flat, dtype=np.float64)
+    tr.begin()
+    P, M, V = dev(flat), torch.zeros(d.n_params, device="cuda"), torch.zeros(d.n_params, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    mk, dk, loss = ops.key_tensor(tr.key), ops.key_tensor(ds.key), torch.zeros(8, device="cuda")
+    mk_job = lambda ws: ops.make_job(odesc_to_c(lib, d), lib.make_data_desc(name, dd, pd), P, M, V, step, mk, dk, None,
+                                     loss, workspace=ws)
+    ws = ops.fused_workspace(mk_job(None))
+    ops.train_fused([mk_job(ws)], 8, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, 0, 8, events=False)
+    assert_params_close(P.cpu().numpy(), tr.params, 8, d.lr, frac=1.0)
+    assert relerr(M.cpu().numpy(), tr.m) <= 2e-5
+
+
+def test_fused_cluster_packed_and_chunked(ops, lib):
+    """Several clusters in one launch == each alone; chunked launches == one launch."""
+    n = 6
+    singles, packed, jobs = [], [], []
+    for case in MLP_CASES[:3] + MLP_CASES[5:]:
+        _, _, _, st, job = mlp_setup(ops, lib, case, n)
+        for chunk in (2, 4):
+            ops.train_fused([job], chunk, ops.fused_scratch(1))
+            torch.cuda.synchronize()
+        singles.append(st)
+        _, _, _, st2, job2 = mlp_setup(ops, lib, case, n)
+        packed.append(st2)
+        jobs.append(job2)
+    ops.train_fused(jobs, n, ops.fused_scratch(len(jobs)))
+    torch.cuda.synchronize()
+    for a, b in zip(singles, packed):
+        for k in ("P", "M", "V", "mk", "dk", "step"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a["loss"][:4], b["loss"][2:6])

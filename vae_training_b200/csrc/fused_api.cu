@@ -1,0 +1,91 @@
+// fused_api.cu -- the fused-training entry points of the C ABI: dispatch between the
+// single-CTA kernel (fused_small.cu, class 1) and the cluster kernel (fused_mlp.cu, class 2).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace vae {
+// fused_small.cu
+int small_supported(const VaeTrainJob* job);
+int small_ctas_per_sm(const VaeTrainJob* job);
+size_t small_job_bytes();
+int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch, cudaStream_t s);
+// fused_mlp.cu
+struct MlpJobDev;
+int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes);
+int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o);
+size_t mlp_job_bytes();
+int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s);
+}  // namespace vae
+
+extern "C" {
+
+int vae_train_fused_supported(const VaeTrainJob* job) {
+  if (!job) return 0;
+  if (vae::small_supported(job)) return 1;
+  return vae::mlp_supported(job, nullptr, nullptr);
+}
+
+size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job) {
+  size_t ws = 0;
+  if (job && !vae::small_supported(job) && vae::mlp_supported(job, nullptr, &ws)) return ws;
+  return 0;
+}
+
+int vae_train_fused_ctas_per_sm(const VaeTrainJob* job) {
+  VAE_REQUIRE(job, "vae_train_fused_ctas_per_sm: job is NULL");
+  if (vae::small_supported(job)) return vae::small_ctas_per_sm(job);
+  return 0;
+}
+
+size_t vae_train_fused_scratch_bytes(int32_t n_jobs) {
+  const size_t per = vae::small_job_bytes() > vae::mlp_job_bytes() ? vae::small_job_bytes() : vae::mlp_job_bytes();
+  return n_jobs > 0 ? (size_t)n_jobs * per : 0;
+}
+
+int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
+                    size_t scratch_bytes, void* stream) {
+  VAE_REQUIRE(jobs && n_jobs > 0 && n_steps >= 0, "vae_train_fused: bad arguments");
+  VAE_REQUIRE(d_scratch && scratch_bytes >= vae_train_fused_scratch_bytes(n_jobs),
+              "vae_train_fused: scratch too small (need %zu bytes)", vae_train_fused_scratch_bytes(n_jobs));
+  if (n_steps == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cls = vae_train_fused_supported(&jobs[0]);
+  for (int i = 0; i < n_jobs; ++i) {
+    const int c = vae_train_fused_supported(&jobs[i]);
+    if (c == 0) {
+      vae::set_error("vae_train_fused: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i, jobs[i].desc.data_dim,
+                     jobs[i].desc.latent_dim, jobs[i].desc.n_enc_hidden, jobs[i].desc.n_dec_hidden);
+      return VAE_ERR_UNSUPPORTED;
+    }
+    VAE_REQUIRE(c == cls, "vae_train_fused: jobs %d and 0 belong to different fused-kernel classes (%d vs %d)", i, c, cls);
+  }
+  if (cls == 1) return vae::small_train_fused(jobs, n_jobs, n_steps, d_scratch, s);
+
+  // class 2: one cluster per model
+  const size_t jb = vae::mlp_job_bytes();
+  char* host = (char*)malloc((size_t)n_jobs * jb);
+  VAE_REQUIRE(host, "vae_train_fused: out of host memory");
+  size_t smem = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const VaeTrainJob& j = jobs[i];
+    size_t sb = 0, wb = 0;
+    vae::mlp_supported(&j, &sb, &wb);
+    if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
+        !j.workspace || (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
+      free(host);
+      vae::set_error("vae_train_fused: job %d has a NULL device pointer (class 2 needs a workspace of "
+                     "vae_train_fused_workspace_bytes() = %zu bytes)", i, wb);
+      return VAE_ERR_INVALID;
+    }
+    if (sb > smem) smem = sb;
+    int rc = vae::mlp_fill_job(j, (vae::MlpJobDev*)(host + (size_t)i * jb));
+    if (rc) { free(host); return rc; }
+  }
+  cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * jb, cudaMemcpyHostToDevice, s);
+  free(host);
+  VAE_CUDA_OK(e);
+  return vae::mlp_launch(d_scratch, n_jobs, smem, n_steps, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,539 @@
+// fused_mlp.cu -- persistent fused training loop for the hidden-layer VAEs of the sphere
+// sweep (sphere_vae_padding_expts.sh: enc = dec = 200|200|200), one thread-block CLUSTER per
+// model.
+//
+// The same hot-loop body as fused_small.cu (model.py:221-222: key splits, eps draw, dataset
+// batch, VAE.apply networks.py:61-84, sampled ELBO :94-98, hand-derived backward, legacy flax
+// Adam), but a 166-176k-parameter model (2 MB with Adam state) does not fit one SM.  The
+// cluster's CS CTAs split every Dense layer by OUTPUT COLUMNS:
+//   forward   Y[:, slice]  = act(X W[:, slice] + b[slice])              X: all rows, all K
+//   backward  dW[:, slice] = X^T dY[:, slice]  (+ Adam on the slice)     the CTA owns its columns
+//             dX[:, kslice] = (dY W[kslice, :]^T) * relu'(X[:, kslice])   dY: all rows, all N
+// Activations and gradients are exchanged through an L2-resident workspace in FEATURE-MAJOR
+// layout ([feature][batch], batch contiguous => 128-bit loads along the batch everywhere) and
+// one hardware cluster barrier per layer phase; weights / Adam moments stay in L2 (they are
+// touched once per step).  Per step the only HBM-bound traffic is the 4-byte loss store.
+//
+// Exact work skipping: the generated batch has exactly-zero padding columns, so encoder layer
+// 0 uses only its first DR input rows and the other rows' gradients (exactly 0) are never
+// formed (Adam leaves those weights bit-for-bit unchanged).
+#include "common.cuh"
+
+namespace vae {
+
+constexpr int kMT = 256;                       // threads per CTA
+constexpr int kML = VAE_MAX_HIDDEN + 1;        // max Dense layers per net
+constexpr int kMlpMaxCluster = 8;
+
+struct MlpJobDev {
+  float* params; float* adam_m; float* adam_v; int32_t* step;
+  uint32_t* model_key; uint32_t* dataset_key; const float* A; float* loss_out; float* ws;
+  int32_t B, BP, D, L, DR, kind, G, dd, tunable, n_enc, n_dec, maxw;
+  int32_t enc_sizes[kML + 1], dec_sizes[kML + 1];
+  int32_t enc_w[kML], enc_b[kML], dec_w[kML], dec_b[kML];
+  int32_t off_lv, off_eps;
+  int32_t ws_zT, ws_gn, ws_enc[kML], ws_dec[kML], ws_g[2], ws_dzs;
+  float eps0, lr, b1, b2, omb1, omb2, adam_eps;
+};
+
+__host__ __device__ constexpr int m_up4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline int m_batch_stride(int B) { int g = (B + 3) / 4; g |= 1; return 4 * g; }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// All threads of all CTAs of the cluster.  release/acquire at cluster scope + a device fence:
+// global writes made before the barrier are visible to every CTA of the cluster after it.
+__device__ __forceinline__ void cluster_barrier() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct Slice { int c0, w; };
+__device__ __forceinline__ Slice slice_of(int n, int rank, int cs) {
+  const int chunk = (n + cs - 1) / cs;
+  int c0 = rank * chunk; if (c0 > n) c0 = n;
+  int c1 = c0 + chunk; if (c1 > n) c1 = n;
+  return Slice{c0, c1 - c0};
+}
+
+// dst (smem, [nrows][BP]) <- src (global, same layout); L1 is bypassed (other CTAs wrote it)
+__device__ __forceinline__ void load_rows(float* dst, const float* src, int nrows, int BP) {
+  const int n4 = (nrows * BP) >> 2;
+  for (int i = threadIdx.x; i < n4; i += kMT) reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+}
+
+// outT[(o0+j)][b] = epi( add[o0+j] + sum_k AT[k][b] * Ws[k][j] ),  j < w, all b.
+//   Ws (smem, [K][W4]) must already be staged; AT smem [K][BP].
+//   relu: max(.,0).  maskT != nullptr: multiply by (maskT[(o0+j)][b] > 0) (relu backward).
+//   Rows b >= B are written as 0.
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, const float* __restrict__ Ws, int W4,
+                                          int w, const float* __restrict__ add_g, int o0, bool relu,
+                                          const float* __restrict__ maskT, float* __restrict__ outT_g, int BP, int B) {
+  const int ncg = W4 >> 2, NG = BP >> 2;
+  for (int tile = threadIdx.x; tile < ncg * NG; tile += kMT) {
+    const int cg = tile / NG, rg = tile - cg * NG;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+    const float* ap = AT + 4 * rg;
+    const float* wp = Ws + 4 * cg;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(ap + k * BP);
+      const float4 wv = *reinterpret_cast<const float4*>(wp + k * W4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[j][r] = fmaf(wj[j], av[r], acc[j][r]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = 4 * cg + j;
+      if (col >= w) continue;
+      const float bias = add_g ? add_g[o0 + col] : 0.f;
+      float o[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float v = acc[j][r] + bias;
+        if (relu) v = fmaxf(v, 0.f);
+        if (maskT) v = maskT[(o0 + col) * BP + 4 * rg + r] > 0.f ? v : 0.f;
+        if (4 * rg + r >= B) v = 0.f;
+        o[r] = v;
+      }
+      *reinterpret_cast<float4*>(outT_g + (size_t)(o0 + col) * BP + 4 * rg) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// Ws[k][j] = Wg[k*N + c0 + j]  (forward / dW column slice), zero padded to W4
+__device__ __forceinline__ void stage_w_cols(float* Ws, const float* Wg, int K, int N, int c0, int w, int W4) {
+  for (int idx = threadIdx.x; idx < K * W4; idx += kMT) {
+    const int k = idx / W4, j = idx - k * W4;
+    Ws[idx] = j < w ? __ldcg(Wg + (size_t)k * N + c0 + j) : 0.f;
+  }
+}
+// Ws[n][j] = Wg[(k0+j)*N + n]   (dX: rows k0..k0+w of W, transposed), zero padded to W4
+__device__ __forceinline__ void stage_w_rows_t(float* Ws, const float* Wg, int N, int k0, int w, int W4) {
+  for (int idx = threadIdx.x; idx < W4 * N; idx += kMT) {
+    const int j = idx / N, n = idx - j * N;
+    Ws[n * W4 + j] = j < w ? __ldcg(Wg + (size_t)(k0 + j) * N + n) : 0.f;
+  }
+}
+
+// dWs[k][j] = sum_b HT[k][b] * dYT[c0+j][b]  (k < K, j < w);  dbs[j] = sum_b dYT[c0+j][b]
+// 4x4 tiles over (k, j); the 4 k-rows of a tile are interleaved (k, k+KT, k+2KT, k+3KT) so
+// the 128-bit loads of a warp's consecutive tiles hit consecutive bank groups.
+__device__ __forceinline__ void tile_dw(const float* __restrict__ HT, int K, const float* __restrict__ dYT, int c0, int w,
+                                        int W4, float* __restrict__ dWs, float* __restrict__ dbs, int BP) {
+  const int KT = (K + 3) >> 2, ncg = W4 >> 2, NG = BP >> 2;
+  for (int tile = threadIdx.x; tile < KT * ncg; tile += kMT) {
+    const int cg = tile / KT, kg = tile - cg * KT;
+    const float* hp[4]; const float* dp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hp[i] = HT + (size_t)min(kg + i * KT, K - 1) * BP;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dp[j] = dYT + (size_t)(c0 + min(4 * cg + j, w - 1)) * BP;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int g = 0; g < NG; ++g) {
+      float4 hv[4], dv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(hp[i] + 4 * g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dv[j] = *reinterpret_cast<const float4*>(dp[j] + 4 * g);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = acc[i][j];
+          a = fmaf(hv[i].x, dv[j].x, a); a = fmaf(hv[i].y, dv[j].y, a);
+          a = fmaf(hv[i].z, dv[j].z, a); a = fmaf(hv[i].w, dv[j].w, a);
+          acc[i][j] = a;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kg + i * KT;
+      if (k >= K) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * cg + j < w) dWs[k * W4 + 4 * cg + j] = acc[i][j];
+    }
+  }
+  for (int j = threadIdx.x; j < w; j += kMT) {
+    const float* dp = dYT + (size_t)(c0 + j) * BP;
+    float a = 0.f;
+    for (int b = 0; b < BP; ++b) a += dp[b];
+    dbs[j] = a;
+  }
+}
+
+struct MlpHyper { float lr, b1, b2, omb1, omb2, eps, ibc1, ibc2; };
+__device__ __forceinline__ void adam_one(float* P, float* M, float* V, size_t i, float g, const MlpHyper& h) {
+  const float m = h.b1 * M[i] + h.omb1 * g;
+  const float v = h.b2 * V[i] + h.omb2 * g * g;
+  M[i] = m; V[i] = v;
+  P[i] = P[i] - h.lr * (m * h.ibc1) / (sqrtf(v * h.ibc2) + h.eps);
+}
+// Adam on this CTA's column slice of a Dense layer (kernel rows < K, and the bias)
+__device__ __forceinline__ void adam_slice(const MlpJobDev& J, int w_off, int b_off, int K, int N, int c0, int w, int W4,
+                                           const float* dWs, const float* dbs, const MlpHyper& h) {
+  for (int idx = threadIdx.x; idx < K * w; idx += kMT) {
+    const int k = idx / w, j = idx - k * w;
+    adam_one(J.params, J.adam_m, J.adam_v, (size_t)w_off + (size_t)k * N + c0 + j, dWs[k * W4 + j], h);
+  }
+  for (int j = threadIdx.x; j < w; j += kMT) adam_one(J.params, J.adam_m, J.adam_v, (size_t)b_off + c0 + j, dbs[j], h);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {   // result valid in every thread
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMT / 32; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(kMT, 1)
+fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ MlpJobDev J;
+  __shared__ float red[kMT / 32];
+  __shared__ uint32_t keys[8];
+  __shared__ float sl_s[64], scal_s[4];
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster_ctarank(), CS = (int)cluster_nctarank();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + blockIdx.x / CS);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < (int)(sizeof(MlpJobDev) / 4); i += kMT) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int B = J.B, BP = J.BP, D = J.D, L = J.L, DR = J.DR, G = J.G, LD = L + D;
+  const int W4max = m_up4((J.maxw + CS - 1) / CS);
+  // shared memory carve-up (floats)
+  float* bufA = sm;                               // [maxw][BP]  layer input (H^T)
+  float* bufB = bufA + (size_t)J.maxw * BP;       // [maxw][BP]  layer output gradient (dY^T)
+  float* Ws = bufB + (size_t)J.maxw * BP;         // [maxw][W4max] staged weights / dW slice
+  float* dbs = Ws + (size_t)J.maxw * W4max;       // [W4max]
+  float* xT = dbs + W4max;                        // [DR][BP]
+  float* z1T = xT + (size_t)DR * BP;              // [L][BP]
+  float* muT = z1T + (size_t)L * BP;              // [L][BP]
+  float* zsT = muT + (size_t)L * BP;              // [L][BP]
+  float* ws = J.ws;
+  for (int i = tid; i < DR * BP; i += kMT) xT[i] = 0.f;
+
+  // key chains (every CTA tracks both redundantly; lanes 0,1 model side, lanes 2,3 dataset side)
+  uint32_t ck0 = 0, ck1 = 0;
+  if (tid < 4) { const uint32_t* src = tid < 2 ? J.model_key : J.dataset_key; ck0 = src[0]; ck1 = src[1]; }
+  const int32_t step0 = J.step[0];
+  double b1t = pow((double)J.b1, (double)step0), b2t = pow((double)J.b2, (double)step0);
+  MlpHyper hp; hp.lr = J.lr; hp.b1 = J.b1; hp.b2 = J.b2; hp.omb1 = J.omb1; hp.omb2 = J.omb2; hp.eps = J.adam_eps;
+  const float invB = 1.0f / (float)B, fB = (float)B;
+  __syncthreads();
+  cluster_barrier();
+
+  for (int64_t s = 0; s < n_steps; ++s) {
+    // ---- keys of this step (vae.py:125, datasets.py:51)
+    if (tid < 4) {
+      uint32_t x0 = (uint32_t)(tid & 1), x1 = (uint32_t)(tid & 1) + 2u;
+      threefry2x32(ck0, ck1, x0, x1);
+      const uint32_t used = tid < 2 ? x0 : x1, carry = tid < 2 ? x1 : x0;
+      const uint32_t other = __shfl_xor_sync(0xFu, carry, 1);
+      ck0 = (tid & 1) ? other : carry; ck1 = (tid & 1) ? carry : other;
+      keys[tid] = used;                            // [lat0 lat1 bat0 bat1]
+    }
+    b1t *= (double)J.b1; b2t *= (double)J.b2;
+    hp.ibc1 = 1.0f / (1.0f - (float)b1t); hp.ibc2 = 1.0f / (1.0f - (float)b2t);
+    // per-step constants from the (possibly just updated) parameters
+    if (tid < L) sl_s[tid] = expf(0.5f * __ldcg(J.params + J.off_lv + tid));
+    if (tid == 0) {
+      const float e = J.tunable ? __ldcg(J.params + J.off_eps) * J.eps0 : J.eps0;
+      scal_s[0] = e; scal_s[1] = expf(0.5f * e); scal_s[2] = expf(-e);
+    }
+    __syncthreads();
+    // ================= phase R: random draws, spread over the whole cluster
+    {
+      const uint32_t lk0 = keys[0], lk1 = keys[1], bk0 = keys[2], bk1 = keys[3];
+      const int n_e = B * LD, half_e = (n_e + 1) >> 1, n_d = B * G, half_d = (n_d + 1) >> 1;
+      float* zT = ws + J.ws_zT; float* gn = ws + J.ws_gn;
+      for (int w = rank * kMT + tid; w < half_e + half_d; w += CS * kMT) {
+        if (w < half_e) {
+          const int j = w, j2 = w + half_e;
+          uint32_t x0 = (uint32_t)j, x1 = j2 < n_e ? (uint32_t)j2 : 0u;
+          threefry2x32(lk0, lk1, x0, x1);
+          { const int r = j / LD; zT[(size_t)(j - r * LD) * BP + r] = normal_from_bits(x0); }
+          if (j2 < n_e) { const int r = j2 / LD; zT[(size_t)(j2 - r * LD) * BP + r] = normal_from_bits(x1); }
+        } else {
+          const int j = w - half_e, j2 = j + half_d;
+          uint32_t x0 = (uint32_t)j, x1 = j2 < n_d ? (uint32_t)j2 : 0u;
+          threefry2x32(bk0, bk1, x0, x1);
+          gn[j] = normal_from_bits(x0);
+          if (j2 < n_d) gn[j2] = normal_from_bits(x1);
+        }
+      }
+    }
+    cluster_barrier();
+    // ---- every CTA: eps rows for the encoder noise, generator transform (bit-exact order)
+    load_rows(z1T, ws + J.ws_zT, L, BP);
+    for (int b = tid; b < B; b += kMT) {
+      const float* gr = ws + J.ws_gn + (size_t)b * G;
+      if (J.kind == VAE_DATA_SPHERE) {
+        float acc = 0.f;
+        for (int j = 0; j < J.dd; ++j) { const float v = __ldcg(gr + j); const float sq = __fmul_rn(v, v); acc = j == 0 ? sq : __fadd_rn(acc, sq); }
+        const float rad = __fsqrt_rn(acc);
+        for (int j = 0; j < J.dd; ++j) xT[j * BP + b] = __fdiv_rn(__ldcg(gr + j), rad);
+      } else if (J.kind == VAE_DATA_LINEAR_GAUSSIAN) {
+        for (int i = 0; i < J.dd; ++i) {
+          float acc = __fmul_rn(J.A[i * G], __ldcg(gr));
+          for (int k = 1; k < G; ++k) acc = __fadd_rn(acc, __fmul_rn(J.A[i * G + k], __ldcg(gr + k)));
+          xT[i * BP + b] = acc;
+        }
+      } else {
+        float acc = 0.f;
+        for (int j = 0; j < J.dd; ++j) { const float v = __ldcg(gr + j); xT[j * BP + b] = v; const float pr = __fmul_rn(v, J.A[j]); acc = j == 0 ? pr : __fadd_rn(acc, pr); }
+        xT[J.dd * BP + b] = det_sigmoid(acc);
+      }
+    }
+    __syncthreads();
+    // ================= encoder forward
+    for (int i = 0; i < J.n_enc; ++i) {
+      const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
+      const Slice sc = slice_of(N, rank, CS);
+      const int W4 = m_up4(sc.w);
+      const float* AT = xT;
+      if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); AT = bufA; }
+      stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
+      __syncthreads();
+      tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
+      cluster_barrier();
+    }
+    // ---- reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
+    load_rows(muT, ws + J.ws_enc[J.n_enc - 1], L, BP);
+    __syncthreads();
+    for (int i = tid; i < L * BP; i += kMT) {
+      const int l = i / BP, b = i - l * BP;
+      zsT[i] = b < B ? fmaf(sl_s[l], z1T[i], muT[i]) : 0.f;
+    }
+    __syncthreads();
+    // ================= decoder forward
+    for (int i = 0; i < J.n_dec; ++i) {
+      const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
+      const Slice sc = slice_of(N, rank, CS);
+      const int W4 = m_up4(sc.w);
+      const float* AT = zsT;
+      if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); AT = bufA; }
+      stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
+      __syncthreads();
+      tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
+      cluster_barrier();
+    }
+    // ================= output, loss, d x_hat (every CTA, all rows; reductions used by CTA 0)
+    {
+      const float e = scal_s[0], sd = scal_s[1], inv_var = scal_s[2];
+      load_rows(bufB, ws + J.ws_dec[J.n_dec - 1], D, BP);      // decoder output
+      load_rows(bufA, ws + J.ws_zT + (size_t)L * BP, D, BP);   // z2^T
+      __syncthreads();
+      float r2 = 0.f, rz = 0.f, mu2 = 0.f;
+      const float gscale = inv_var * invB;
+      for (int i = tid; i < D * BP; i += kMT) {
+        const int d = i / BP, b = i - d * BP;
+        float g = 0.f;
+        if (b < B) {
+          const float z2 = bufA[i];
+          const float xh = fmaf(z2, sd, bufB[i]);
+          const float r = xh - (d < DR ? xT[i] : 0.f);
+          r2 = fmaf(r, r, r2); rz = fmaf(r, z2, rz);
+          g = r * gscale;
+        }
+        bufB[i] = g;                                           // dY^T of the last decoder layer
+      }
+      if (rank == 0) {
+        for (int i = tid; i < L * BP; i += kMT) { const int b = i % BP; if (b < B) mu2 = fmaf(muT[i], muT[i], mu2); }
+        const float s_r2 = block_sum(r2, red), s_rz = block_sum(rz, red), s_mu2 = block_sum(mu2, red);
+        if (tid == 0) {
+          float klc = 0.f;
+          for (int l = 0; l < L; ++l) { const float lv = __ldcg(J.params + J.off_lv + l); klc += 1.f + lv - expf(lv); }
+          const float dkl = (-0.5f * klc * fB + 0.5f * s_mu2) * invB;
+          const float mse = (0.5f * inv_var * s_r2 + 0.5f * (1.8378770664093453f + e) * fB * (float)D) * invB;
+          J.loss_out[s] = dkl + mse;
+          if (J.tunable) {
+            const float g = J.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
+            adam_one(J.params, J.adam_m, J.adam_v, (size_t)J.off_eps, g, hp);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ================= decoder backward (dY^T of layer i in bufB, all N rows)
+    int pp = 0;
+    for (int i = J.n_dec - 1; i >= 0; --i) {
+      const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
+      const float* HT = zsT;
+      if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); HT = bufA; }
+      // dX slice: rows k0..k0+kw of the layer input
+      const Slice sk = slice_of(K, rank, CS);
+      const int K4 = m_up4(sk.w);
+      stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
+      __syncthreads();
+      float* dst = i > 0 ? ws + J.ws_g[pp] : ws + J.ws_dzs;
+      tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
+      __syncthreads();
+      // dW slice: columns c0..c0+w of the layer output
+      const Slice sc = slice_of(N, rank, CS);
+      const int W4 = m_up4(sc.w);
+      if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+      cluster_barrier();
+      adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+      __syncthreads();
+      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
+      __syncthreads();
+    }
+    // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
+    load_rows(bufB, ws + J.ws_dzs, L, BP);
+    __syncthreads();
+    if (rank == 0) {
+      // g_lv[l] = sum_b dzs*z1 * 0.5*s_l - 0.5*(1 - e^lv_l): one warp per l
+      for (int l = tid >> 5; l < L; l += kMT / 32) {
+        float a = 0.f;
+        for (int b = tid & 31; b < B; b += 32) a = fmaf(bufB[l * BP + b], z1T[l * BP + b], a);
+        a = warp_sum(a);
+        if ((tid & 31) == 0) {
+          const float lv = __ldcg(J.params + J.off_lv + l);
+          adam_one(J.params, J.adam_m, J.adam_v, (size_t)J.off_lv + l, a * 0.5f * sl_s[l] - 0.5f * (1.f - expf(lv)), hp);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < L * BP; i += kMT) { const int b = i % BP; bufB[i] = b < B ? fmaf(muT[i], invB, bufB[i]) : 0.f; }
+    __syncthreads();
+    // ================= encoder backward
+    for (int i = J.n_enc - 1; i >= 0; --i) {
+      const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
+      const float* HT = xT;
+      if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); HT = bufA; }
+      __syncthreads();
+      if (i > 0) {
+        const Slice sk = slice_of(K, rank, CS);
+        const int K4 = m_up4(sk.w);
+        stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
+        __syncthreads();
+        tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
+        __syncthreads();
+      }
+      const Slice sc = slice_of(N, rank, CS);
+      const int W4 = m_up4(sc.w);
+      if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+      if (i > 0) cluster_barrier(); else __syncthreads();
+      adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+      __syncthreads();
+      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
+      __syncthreads();
+    }
+    // the next step's phase-R barrier orders this step's parameter writes before any read
+  }
+  cluster_barrier();
+  if (rank == 0) {
+    if (tid == 0) J.step[0] = step0 + (int32_t)n_steps;
+    if (tid < 4 && (tid & 1) == 0) { uint32_t* dst = tid < 2 ? J.model_key : J.dataset_key; dst[0] = ck0; dst[1] = ck1; }
+  }
+}
+
+// ------------------------------------------------------------------------ host side
+static size_t mlp_smem_bytes(int maxw, int BP, int DR, int L, int cs) {
+  const int W4max = m_up4((maxw + cs - 1) / cs);
+  return sizeof(float) * ((size_t)2 * maxw * BP + (size_t)maxw * W4max + W4max + (size_t)DR * BP + (size_t)3 * L * BP);
+}
+
+static size_t mlp_ws_floats(const Layout& Lo, const VaeDesc& d, const VaeDataDesc& g, MlpJobDev* o) {
+  const int BP = m_batch_stride(d.batch);
+  const int gg = g.kind == VAE_DATA_LINEAR_GAUSSIAN ? g.intrinsic_dim : g.dim;
+  size_t off = 0;
+  auto take = [&](size_t n) { const size_t r = off; off += (n + 3) & ~(size_t)3; return (int32_t)r; };
+  const int32_t zT = take((size_t)(d.latent_dim + d.data_dim) * BP);
+  const int32_t gn = take((size_t)d.batch * gg);
+  int32_t enc[kML], dec[kML];
+  for (int i = 0; i < Lo.n_enc; ++i) enc[i] = take((size_t)Lo.enc_sizes[i + 1] * BP);
+  for (int i = 0; i < Lo.n_dec; ++i) dec[i] = take((size_t)Lo.dec_sizes[i + 1] * BP);
+  const int32_t g0 = take((size_t)Lo.max_width * BP), g1 = take((size_t)Lo.max_width * BP);
+  const int32_t dz = take((size_t)d.latent_dim * BP);
+  if (o) {
+    o->ws_zT = zT; o->ws_gn = gn; o->ws_g[0] = g0; o->ws_g[1] = g1; o->ws_dzs = dz;
+    for (int i = 0; i < Lo.n_enc; ++i) o->ws_enc[i] = enc[i];
+    for (int i = 0; i < Lo.n_dec; ++i) o->ws_dec[i] = dec[i];
+  }
+  return off;
+}
+
+// 2 if the job can run on the cluster kernel, else 0
+int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes) {
+  const VaeDesc& d = j->desc;
+  const VaeDataDesc& g = j->data;
+  if (d.n_enc_hidden + d.n_dec_hidden == 0 || d.sig_decoder) return 0;
+  if ((d.sig_decoder != 0) != (g.kind == VAE_DATA_SIGMOID)) return 0;
+  Layout Lo;
+  if (make_layout(&d, &Lo)) return 0;
+  const int width = g.dim + g.padding_dim + (g.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  if (width != d.data_dim || d.latent_dim > 64 || d.batch > 4096) return 0;
+  if (Lo.n_params >= (1ll << 31)) return 0;
+  const int BP = m_batch_stride(d.batch);
+  const int dr = g.dim + (g.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  const size_t sb = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpMaxCluster);
+  if (sb > (size_t)227 * 1024 - 2048) return 0;
+  if (smem) *smem = sb;
+  if (ws_bytes) *ws_bytes = mlp_ws_floats(Lo, d, g, nullptr) * sizeof(float);
+  return 2;
+}
+
+int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o) {
+  Layout Lo;
+  int rc = make_layout(&j.desc, &Lo);
+  if (rc) return rc;
+  memset(o, 0, sizeof(*o));
+  o->params = j.params; o->adam_m = j.adam_m; o->adam_v = j.adam_v; o->step = j.step;
+  o->model_key = j.model_key; o->dataset_key = j.dataset_key; o->A = j.A; o->loss_out = j.loss_out;
+  o->ws = (float*)j.workspace;
+  o->B = j.desc.batch; o->BP = m_batch_stride(j.desc.batch); o->D = j.desc.data_dim; o->L = j.desc.latent_dim;
+  o->kind = j.data.kind; o->dd = j.data.dim;
+  o->DR = j.data.dim + (j.data.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  o->G = j.data.kind == VAE_DATA_LINEAR_GAUSSIAN ? j.data.intrinsic_dim : j.data.dim;
+  o->tunable = j.desc.tunable_decoder_var; o->n_enc = Lo.n_enc; o->n_dec = Lo.n_dec; o->maxw = Lo.max_width;
+  for (int i = 0; i <= Lo.n_enc; ++i) o->enc_sizes[i] = Lo.enc_sizes[i];
+  for (int i = 0; i <= Lo.n_dec; ++i) o->dec_sizes[i] = Lo.dec_sizes[i];
+  for (int i = 0; i < Lo.n_enc; ++i) { o->enc_w[i] = (int32_t)Lo.enc_w[i]; o->enc_b[i] = (int32_t)Lo.enc_b[i]; }
+  for (int i = 0; i < Lo.n_dec; ++i) { o->dec_w[i] = (int32_t)Lo.dec_w[i]; o->dec_b[i] = (int32_t)Lo.dec_b[i]; }
+  o->off_lv = (int32_t)Lo.off_eps_p; o->off_eps = (int32_t)Lo.off_eps;
+  mlp_ws_floats(Lo, j.desc, j.data, o);
+  const AdamHyper hp = make_adam_hyper(&j.desc);
+  o->eps0 = (float)j.desc.epsilon0; o->lr = hp.lr; o->b1 = hp.b1; o->b2 = hp.b2; o->omb1 = hp.omb1; o->omb2 = hp.omb2;
+  o->adam_eps = hp.eps;
+  return 0;
+}
+
+size_t mlp_job_bytes() { return sizeof(MlpJobDev); }
+
+int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s) {
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_jobs * kMlpMaxCluster), 1, 1);
+  cfg.blockDim = dim3(kMT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kMlpMaxCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)d_jobs, n_steps));
+  return 0;
+}
+
+}  // namespace vae

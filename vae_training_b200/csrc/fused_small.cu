@@ -619,76 +619,66 @@ static int occupancy_small(int shape_id, size_t smem, int* out) {
 
 }  // namespace vae
 
-extern "C" {
+namespace vae {
 
-int vae_train_fused_ctas_per_sm(const VaeTrainJob* job) {
-  VAE_REQUIRE(job, "vae_train_fused_ctas_per_sm: job is NULL");
+int small_ctas_per_sm(const VaeTrainJob* job) {
   int fl = 0, out = 0;
-  const int id = vae::small_shape_of(job, &fl);
-  if (id < 0 || (size_t)fl * 4 > (size_t)vae::kMaxSmem) return 0;
-  const int rc = vae::occupancy_small(id, (size_t)fl * sizeof(float), &out);
+  const int id = small_shape_of(job, &fl);
+  if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) return 0;
+  const int rc = occupancy_small(id, (size_t)fl * sizeof(float), &out);
   return rc ? rc : out;
 }
 
-int vae_train_fused_supported(const VaeTrainJob* job) {
+int small_supported(const VaeTrainJob* job) {
   if (!job) return 0;
   int fl = 0;
-  const int id = vae::small_shape_of(job, &fl);
-  if (id < 0 || (size_t)fl * 4 > (size_t)vae::kMaxSmem) return 0;
+  const int id = small_shape_of(job, &fl);
+  if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) return 0;
   return 1;
 }
 
-size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job) { (void)job; return 0; }
 
-size_t vae_train_fused_scratch_bytes(int32_t n_jobs) {
-  return n_jobs > 0 ? (size_t)n_jobs * sizeof(vae::FusedJobDev) : 0;
-}
+size_t small_job_bytes() { return sizeof(FusedJobDev); }
 
-int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
-                    size_t scratch_bytes, void* stream) {
-  VAE_REQUIRE(jobs && n_jobs > 0 && n_steps >= 0, "vae_train_fused: bad arguments");
-  VAE_REQUIRE(d_scratch && scratch_bytes >= vae_train_fused_scratch_bytes(n_jobs),
-              "vae_train_fused: scratch too small (need %zu bytes)", vae_train_fused_scratch_bytes(n_jobs));
-  if (n_steps == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  vae::FusedJobDev* host = (vae::FusedJobDev*)malloc((size_t)n_jobs * sizeof(vae::FusedJobDev));
+int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch, cudaStream_t s) {
+  FusedJobDev* host = (FusedJobDev*)malloc((size_t)n_jobs * sizeof(FusedJobDev));
   VAE_REQUIRE(host, "vae_train_fused: out of host memory");
   int max_fl = 0;
   bool homogeneous = true;
   for (int i = 0; i < n_jobs; ++i) {
     const VaeTrainJob& j = jobs[i];
     int fl = 0;
-    const int id = vae::small_shape_of(&j, &fl);
-    if (id < 0 || (size_t)fl * 4 > (size_t)vae::kMaxSmem) {
+    const int id = small_shape_of(&j, &fl);
+    if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) {
       free(host);
-      vae::set_error("vae_train_fused: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i,
+      set_error("vae_train_fused: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i,
                      j.desc.data_dim, j.desc.latent_dim, j.desc.n_enc_hidden, j.desc.n_dec_hidden);
       return VAE_ERR_UNSUPPORTED;
     }
     if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
         (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
       free(host);
-      vae::set_error("vae_train_fused: job %d has a NULL device pointer", i);
+      set_error("vae_train_fused: job %d has a NULL device pointer", i);
       return VAE_ERR_INVALID;
     }
     if (fl > max_fl) max_fl = fl;
-    vae::FusedJobDev& o = host[i];
+    FusedJobDev& o = host[i];
     o.params = j.params; o.adam_m = j.adam_m; o.adam_v = j.adam_v; o.step = j.step;
     o.model_key = j.model_key; o.dataset_key = j.dataset_key; o.A = j.A; o.loss_out = j.loss_out;
     o.batch = j.desc.batch; o.tunable = j.desc.tunable_decoder_var; o.shape_id = id; o.pad_ = 0;
-    const vae::AdamHyper hp = vae::make_adam_hyper(&j.desc);
+    const AdamHyper hp = make_adam_hyper(&j.desc);
     o.eps0 = (float)j.desc.epsilon0; o.lr = hp.lr; o.b1 = hp.b1; o.b2 = hp.b2; o.omb1 = hp.omb1; o.omb2 = hp.omb2;
     o.adam_eps = hp.eps;
     if (id != host[0].shape_id || o.batch != host[0].batch) homogeneous = false;
   }
   // pageable-source async copies are staged before the call returns, so `host` may be freed
-  cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * sizeof(vae::FusedJobDev),
+  cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * sizeof(FusedJobDev),
                                   cudaMemcpyHostToDevice, s);
   const int shape0 = host[0].shape_id;
   free(host);
   VAE_CUDA_OK(e);
-  return vae::launch_small(shape0, homogeneous, n_jobs, (size_t)max_fl * sizeof(float),
-                           (const vae::FusedJobDev*)d_scratch, n_steps, s);
+  return launch_small(shape0, homogeneous, n_jobs, (size_t)max_fl * sizeof(float),
+                           (const FusedJobDev*)d_scratch, n_steps, s);
 }
 
-}  // extern "C"
+}  // namespace vae

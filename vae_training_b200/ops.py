@@ -205,7 +205,14 @@ def make_job(desc: VaeDesc, data: VaeDataDesc, params, adam_m, adam_v, step, mod
 
 
 def fused_supported(job: VaeTrainJob) -> int:
+    """0: no fused kernel; 1: single-CTA kernel; 2: thread-block-cluster kernel (needs a workspace)."""
     return int(_lib.load().vae_train_fused_supported(C.byref(job)))
+
+
+def fused_workspace(job: VaeTrainJob, device="cuda") -> Optional[torch.Tensor]:
+    """Device workspace a class-2 job needs (None when the kernel needs none)."""
+    n = int(_lib.load().vae_train_fused_workspace_bytes(C.byref(job)))
+    return torch.zeros((n,), dtype=torch.uint8, device=device) if n > 0 else None
 
 
 def fused_ctas_per_sm(job: VaeTrainJob) -> int:

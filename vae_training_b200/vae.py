@@ -89,7 +89,12 @@ class VAEModel:
         self._scratch = ops.fused_scratch(1, device)
         self._job = ops.make_job(self.desc, dataset.data_desc(), self.params, self.adam_m, self.adam_v, self.step,
                                  self.key, dataset.key, dataset.A, self._chunk_loss)
-        self.fused = ops.fused_supported(self._job) > 0
+        self.fused_class = ops.fused_supported(self._job)
+        self.fused = self.fused_class > 0
+        self._fused_ws = ops.fused_workspace(self._job, device) if self.fused else None
+        if self._fused_ws is not None:
+            self._job = ops.make_job(self.desc, dataset.data_desc(), self.params, self.adam_m, self.adam_v, self.step,
+                                     self.key, dataset.key, dataset.A, self._chunk_loss, workspace=self._fused_ws)
         # vae_losses interleaves train and eval losses (vae.py:130,136): kept as device pieces
         self._loss_pieces: List[torch.Tensor] = []
         self.var_enc: List[torch.Tensor] = []
@@ -266,11 +271,14 @@ def train_many(models: Sequence[VAEModel], save=True):
     """Packed sweep: every model follows its own reference schedule, but all models whose
     shape has a fused kernel advance together, one persistent launch per chunk (one CTA per
     model).  Models stay step-aligned; a chunk ends at the nearest event of any model."""
-    fused = [m for m in models if m.fused]
     other = [m for m in models if not m.fused]
     for m in models:
         m.begin()
-    if fused:
+    # one pack per fused-kernel class (single-CTA models / cluster models)
+    for cls in (1, 2):
+        fused = [m for m in models if m.fused_class == cls]
+        if not fused:
+            continue
         scratch = ops.fused_scratch(len(fused), fused[0].device)
         b = 0
         while True:
