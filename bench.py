@@ -36,10 +36,12 @@ METRIC = "vae_train_steps_per_sec_summed_over_packed_models"
 UNIT = "train-steps/s"
 
 WORKLOADS = {
-    # name: (dataset, dd, pd, L, lr, eps0, first dataset seed, reference line)
-    "sigmoid_dd3_pd3_ld6": ("sigmoid", 3, 3, 6, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:1"),
-    "sigmoid_dd7_pd20_ld24": ("sigmoid", 7, 20, 24, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:6"),
-    "linear_dd3_pd9_ld20": ("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2, "seed_linpadding_expts.sh:1"),
+    # name: (dataset, dd, pd, L, lr, eps0, first dataset seed, reference line, hidden)
+    "sigmoid_dd3_pd3_ld6": ("sigmoid", 3, 3, 6, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:1", ()),
+    "sigmoid_dd7_pd20_ld24": ("sigmoid", 7, 20, 24, 1e-4, -3.0, 69, "sigmoid_vae_padding_expts.sh:6", ()),
+    "linear_dd3_pd9_ld20": ("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2, "seed_linpadding_expts.sh:1", ()),
+    "sphere_dd3_pd3_ld6": ("sphere", 3, 3, 6, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:1", (200, 200, 200)),
+    "sphere_dd5_pd16_ld16": ("sphere", 5, 16, 16, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:3", (200, 200, 200)),
 }
 
 
@@ -58,8 +60,9 @@ def parse():
 
 def make_specs(workload, n_models, first_index=0):
     from vae_training_b200.packed import RunSpec
-    name, dd, pd, L, lr, eps0, seed0, _ = WORKLOADS[workload]
+    name, dd, pd, L, lr, eps0, seed0, _, hidden = WORKLOADS[workload]
     return [RunSpec(dataset=name, dataset_dimension=dd, padding_dim=pd, latent_dimension=L, learning_rate=lr,
+                    layer_sizes=hidden, encoder_layer_sizes=hidden,
                     epsilon=eps0, tunable_decoder_var=True, dataset_seed=seed0 + first_index + i,
                     name=f"{workload}_ds{seed0 + first_index + i}") for i in range(n_models)]
 
@@ -122,11 +125,11 @@ def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50):
     from oracle import datasets as ods
     from oracle import jax_random as jr
     from oracle import vae_step as vs
-    name, dd, pd, L, lr, eps0, seed0, _ = WORKLOADS[workload]
+    name, dd, pd, L, lr, eps0, seed0, _, hidden = WORKLOADS[workload]
     jobs = []
     for i in range(n_models):
         ds = ods.make_dataset(name, seed0 + i, dd, pd)
-        d = vs.VaeDesc(100, ds.ndim, L, sig_decoder=(name == "sigmoid"), epsilon0=eps0, lr=lr)
+        d = vs.VaeDesc(100, ds.ndim, L, list(hidden), list(hidden), sig_decoder=(name == "sigmoid"), epsilon0=eps0, lr=lr)
         flat = vs.init_params(d, 0)
         key = jr.PRNGKey(0)
         _, key = jr.model_chain_next(key)
@@ -144,8 +147,8 @@ def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50):
 def cpu_baseline(workload, target_seconds):
     cores = os.cpu_count() or 1
     n_models = cores
-    rate, _ = cpu_oracle_run(workload, n_models, 300, cores, warm_steps=20)       # calibrate
-    n_steps = max(200, int(rate * target_seconds / n_models))
+    rate, _ = cpu_oracle_run(workload, n_models, 40, cores, warm_steps=5)         # calibrate
+    n_steps = max(20, int(rate * target_seconds / n_models))
     rate, dt = cpu_oracle_run(workload, n_models, n_steps, cores)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_models} independent {workload} runs x {n_steps} steps, oracle/c (plain C, float32, "
@@ -158,7 +161,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_models = cores
-    rate, _ = cpu_oracle_run(args.workload, n_models, 300, cores, warm_steps=20)
+    rate, _ = cpu_oracle_run(args.workload, n_models, 40, cores, warm_steps=5)
     # each "step" of this arm = one train step of each of n_models models; bound the run to ~minutes
     k = max(1, min(args.steps, int(rate * 20.0 / n_models)))
     w = max(3, min(args.warmup, max(3, k // 10)))
@@ -197,7 +200,7 @@ def run_b200(args):
         n_models = args.models
     else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
         probe = PackedRuns(make_specs(args.workload, 1), max_chunk=4)
-        n_models = n_sm * max(1, ops.fused_ctas_per_sm(probe.jobs[0]))
+        n_models = max(1, ops.fused_resident_jobs(probe.jobs[0]))
         del probe
     specs = make_specs(args.workload, n_models, first_index=rank * n_models)
     runs = PackedRuns(specs, max_chunk=max(K, W))
@@ -274,7 +277,7 @@ def run_b200(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "samples_per_sec": value * spec.batch_size,
-            "config": {"workload": f"{args.workload} ({wl[7]}; BASELINE.json configs[1] shape) x {n_models} "
+            "config": {"workload": f"{args.workload} ({wl[7]}; BASELINE.json {'configs[2]' if wl[8] else 'configs[1]'} shape) x {n_models} "
                                    f"independent dataset seeds packed per GPU", "batch": spec.batch_size,
                        "models_per_gpu": n_models, "data_dim": spec.data_dim, "latent_dim": spec.latent_dimension,
                        "l2_flush": "n/a: working set is SM-resident (shared memory); HBM traffic is the 4-byte "

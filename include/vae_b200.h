@@ -187,6 +187,9 @@ size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job);
 /* Resident CTAs (= models) per SM of the job's fused kernel on the current device: the
  * pack size that fills the GPU is this x the SM count.  0 if unsupported, <0 on error. */
 int vae_train_fused_ctas_per_sm(const VaeTrainJob* job);
+/* Jobs of this shape that are resident at once on the current device (CTAs per SM x SMs for
+ * class 1, co-resident clusters for class 2): the pack size that fills the GPU. */
+int vae_train_fused_resident_jobs(const VaeTrainJob* job);
 /* Device scratch the launch needs for its job table. */
 size_t vae_train_fused_scratch_bytes(int32_t n_jobs);
 /* jobs: HOST array of n_jobs descriptors, all of the same vae_train_fused_supported()

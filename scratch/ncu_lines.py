@@ -63,7 +63,8 @@ def region(ln):
     try: _mk
     except NameError:
         _mk = {"common.cuh": marks("/root/repo/vae_training_b200/csrc/common.cuh", [("threefry", "void threefry2x32("), ("threefry", "void threefry2x32_x2("), ("split", "void split2("), ("log1p", "float neg_log1p_neg("), ("erfinv", "float erf_inv_f32("), ("normal", "float normal_from_bits("), ("normal_fast", "float normal_from_bits_fast("), ("det_exp", "float det_expf("), ("warp_sum", "float warp_sum("), ("hosthelpers", "struct AdamHyper")]),
-               "fused_small.cu": marks("/root/repo/vae_training_b200/csrc/fused_small.cu", [("init", "---- load state"), ("phaseA", "phase A: random"), ("phaseB", "phase B: one thread"), ("phaseC", "phase C: gradient"), ("store", "---- store state"), ("pre", "namespace vae {")])}
+               "fused_small.cu": marks("/root/repo/vae_training_b200/csrc/fused_small.cu", [("init", "---- load state"), ("phaseA", "phase A: random"), ("phaseB", "phase B: one thread"), ("phaseC", "phase C: gradient"), ("store", "---- store state"), ("pre", "namespace vae {")]),
+               "fused_mlp.cu": marks("/root/repo/vae_training_b200/csrc/fused_mlp.cu", [("pre", "namespace vae {"), ("barrier", "void cluster_barrier()"), ("slice", "struct Slice"), ("load_rows", "void load_rows("), ("tile_gemm", "void tile_gemm("), ("stage_cols", "void stage_w_cols("), ("stage_rows_t", "void stage_w_rows_t("), ("tile_dw", "void tile_dw("), ("adam", "struct MlpHyper"), ("block_sum", "float block_sum("), ("kernel_init", "fused_mlp_kernel(const"), ("phaseR", "phase R: random"), ("xform", "every CTA: eps rows"), ("enc_fwd", "= encoder forward"), ("reparam", "---- reparameterise"), ("dec_fwd", "= decoder forward"), ("output", "= output, loss"), ("dec_bwd", "= decoder backward"), ("latent", "= latent: d lv"), ("enc_bwd", "= encoder backward"), ("host", "---- host side")])}
     if f in _mk:
         r = "pre"
         for k, name in _mk[f]:

@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "vae_train_fused_supported": (C.c_int, [C.POINTER(VaeTrainJob)]),
     "vae_train_fused_workspace_bytes": (C.c_size_t, [C.POINTER(VaeTrainJob)]),
     "vae_train_fused_ctas_per_sm": (C.c_int, [C.POINTER(VaeTrainJob)]),
+    "vae_train_fused_resident_jobs": (C.c_int, [C.POINTER(VaeTrainJob)]),
     "vae_train_fused_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "vae_train_fused": (C.c_int, [C.POINTER(VaeTrainJob), C.c_int32, C.c_int64, _P, C.c_size_t, _P]),
     "vae_last_error": (C.c_char_p, []),

@@ -16,6 +16,7 @@ int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes);
 int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o);
 size_t mlp_job_bytes();
 int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s);
+int mlp_resident_jobs(size_t smem, int* out);
 }  // namespace vae
 
 extern "C" {
@@ -36,6 +37,23 @@ int vae_train_fused_ctas_per_sm(const VaeTrainJob* job) {
   VAE_REQUIRE(job, "vae_train_fused_ctas_per_sm: job is NULL");
   if (vae::small_supported(job)) return vae::small_ctas_per_sm(job);
   return 0;
+}
+
+int vae_train_fused_resident_jobs(const VaeTrainJob* job) {
+  VAE_REQUIRE(job, "vae_train_fused_resident_jobs: job is NULL");
+  if (vae::small_supported(job)) {
+    const int per_sm = vae::small_ctas_per_sm(job);
+    if (per_sm <= 0) return per_sm;
+    int dev = 0, sms = 0;
+    VAE_CUDA_OK(cudaGetDevice(&dev));
+    VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return per_sm * sms;
+  }
+  size_t smem = 0;
+  if (!vae::mlp_supported(job, &smem, nullptr)) return 0;
+  int out = 0;
+  const int rc = vae::mlp_resident_jobs(smem, &out);
+  return rc ? rc : out;
 }
 
 size_t vae_train_fused_scratch_bytes(int32_t n_jobs) {

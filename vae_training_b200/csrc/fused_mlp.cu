@@ -56,10 +56,25 @@ __device__ __forceinline__ Slice slice_of(int n, int rank, int cs) {
   return Slice{c0, c1 - c0};
 }
 
-// dst (smem, [nrows][BP]) <- src (global, same layout); L1 is bypassed (other CTAs wrote it)
+// Asynchronous global -> shared copies (LDGSTS): every copy of a staging loop is in flight at
+// once, so a whole operand costs about one L2 round trip instead of one per loop iteration.
+// Data written by other CTAs of the cluster is only read after a cluster barrier (release /
+// acquire at cluster scope; the barrier also invalidates L1).
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// dst (smem, [nrows][BP]) <- src (global, same layout), asynchronous: cp_async_wait_all() +
+// __syncthreads() before use
 __device__ __forceinline__ void load_rows(float* dst, const float* src, int nrows, int BP) {
   const int n4 = (nrows * BP) >> 2;
-  for (int i = threadIdx.x; i < n4; i += kMT) reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+  for (int i = threadIdx.x; i < n4; i += kMT) cp_async16(dst + 4 * i, src + 4 * i);
 }
 
 // outT[(o0+j)][b] = epi( add[o0+j] + sum_k AT[k][b] * Ws[k][j] ),  j < w, all b.
@@ -113,14 +128,14 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, c
 __device__ __forceinline__ void stage_w_cols(float* Ws, const float* Wg, int K, int N, int c0, int w, int W4) {
   for (int idx = threadIdx.x; idx < K * W4; idx += kMT) {
     const int k = idx / W4, j = idx - k * W4;
-    Ws[idx] = j < w ? __ldcg(Wg + (size_t)k * N + c0 + j) : 0.f;
+    if (j < w) cp_async4(Ws + idx, Wg + (size_t)k * N + c0 + j); else Ws[idx] = 0.f;
   }
 }
 // Ws[n][j] = Wg[(k0+j)*N + n]   (dX: rows k0..k0+w of W, transposed), zero padded to W4
 __device__ __forceinline__ void stage_w_rows_t(float* Ws, const float* Wg, int N, int k0, int w, int W4) {
   for (int idx = threadIdx.x; idx < W4 * N; idx += kMT) {
     const int j = idx / N, n = idx - j * N;
-    Ws[n * W4 + j] = j < w ? __ldcg(Wg + (size_t)(k0 + j) * N + n) : 0.f;
+    if (j < w) cp_async4(Ws + n * W4 + j, Wg + (size_t)(k0 + j) * N + n); else Ws[n * W4 + j] = 0.f;
   }
 }
 
@@ -176,20 +191,44 @@ __device__ __forceinline__ void tile_dw(const float* __restrict__ HT, int K, con
 }
 
 struct MlpHyper { float lr, b1, b2, omb1, omb2, eps, ibc1, ibc2; };
+__device__ __forceinline__ float m_approx_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void adam_one(float* P, float* M, float* V, size_t i, float g, const MlpHyper& h) {
   const float m = h.b1 * M[i] + h.omb1 * g;
   const float v = h.b2 * V[i] + h.omb2 * g * g;
   M[i] = m; V[i] = v;
-  P[i] = P[i] - h.lr * (m * h.ibc1) / (sqrtf(v * h.ibc2) + h.eps);
+  P[i] = P[i] - __fdividef(h.lr * (m * h.ibc1), m_approx_sqrt(v * h.ibc2) + h.eps);
 }
-// Adam on this CTA's column slice of a Dense layer (kernel rows < K, and the bias)
+// Adam on this CTA's column slice of a Dense layer (kernel rows < K, and the bias).  The
+// moments live in L2: each thread first issues the loads of kAB parameters, then updates
+// (memory-level parallelism instead of one L2 round trip per parameter).
+constexpr int kAB = 8;
 __device__ __forceinline__ void adam_slice(const MlpJobDev& J, int w_off, int b_off, int K, int N, int c0, int w, int W4,
                                            const float* dWs, const float* dbs, const MlpHyper& h) {
-  for (int idx = threadIdx.x; idx < K * w; idx += kMT) {
-    const int k = idx / w, j = idx - k * w;
-    adam_one(J.params, J.adam_m, J.adam_v, (size_t)w_off + (size_t)k * N + c0 + j, dWs[k * W4 + j], h);
+  float* __restrict__ P = J.params; float* __restrict__ M = J.adam_m; float* __restrict__ V = J.adam_v;
+  const int total = K * w;
+  for (int base = 0; base < total; base += kAB * kMT) {
+    size_t gi[kAB]; float p[kAB], m[kAB], v[kAB], g[kAB]; bool ok[kAB];
+#pragma unroll
+    for (int u = 0; u < kAB; ++u) {
+      const int idx = base + u * kMT + (int)threadIdx.x;
+      ok[u] = idx < total;
+      const int ii = ok[u] ? idx : 0;
+      const int k = ii / w, j = ii - k * w;
+      gi[u] = (size_t)w_off + (size_t)k * N + c0 + j;
+      g[u] = dWs[k * W4 + j];
+      p[u] = __ldcg(P + gi[u]); m[u] = __ldcg(M + gi[u]); v[u] = __ldcg(V + gi[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kAB; ++u) {
+      const float mn = h.b1 * m[u] + h.omb1 * g[u];
+      const float vn = h.b2 * v[u] + h.omb2 * g[u] * g[u];
+      if (ok[u]) {
+        M[gi[u]] = mn; V[gi[u]] = vn;
+        P[gi[u]] = p[u] - __fdividef(h.lr * (mn * h.ibc1), m_approx_sqrt(vn * h.ibc2) + h.eps);
+      }
+    }
   }
-  for (int j = threadIdx.x; j < w; j += kMT) adam_one(J.params, J.adam_m, J.adam_v, (size_t)b_off + c0 + j, dbs[j], h);
+  for (int j = threadIdx.x; j < w; j += kMT) adam_one(P, M, V, (size_t)b_off + c0 + j, dbs[j], h);
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red) {   // result valid in every thread
@@ -284,7 +323,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
     }
     cluster_barrier();
     // ---- every CTA: eps rows for the encoder noise, generator transform (bit-exact order)
-    load_rows(z1T, ws + J.ws_zT, L, BP);
+    load_rows(z1T, ws + J.ws_zT, L, BP);      // waited for before the reparameterisation
     for (int b = tid; b < B; b += kMT) {
       const float* gr = ws + J.ws_gn + (size_t)b * G;
       if (J.kind == VAE_DATA_SPHERE) {
@@ -313,13 +352,13 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const float* AT = xT;
       if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); AT = bufA; }
       stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
       tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
       cluster_barrier();
     }
     // ---- reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
     load_rows(muT, ws + J.ws_enc[J.n_enc - 1], L, BP);
-    __syncthreads();
+    cp_async_wait_all(); __syncthreads();
     for (int i = tid; i < L * BP; i += kMT) {
       const int l = i / BP, b = i - l * BP;
       zsT[i] = b < B ? fmaf(sl_s[l], z1T[i], muT[i]) : 0.f;
@@ -333,7 +372,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const float* AT = zsT;
       if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); AT = bufA; }
       stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
       tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
       cluster_barrier();
     }
@@ -342,7 +381,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const float e = scal_s[0], sd = scal_s[1], inv_var = scal_s[2];
       load_rows(bufB, ws + J.ws_dec[J.n_dec - 1], D, BP);      // decoder output
       load_rows(bufA, ws + J.ws_zT + (size_t)L * BP, D, BP);   // z2^T
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
       float r2 = 0.f, rz = 0.f, mu2 = 0.f;
       const float gscale = inv_var * invB;
       for (int i = tid; i < D * BP; i += kMT) {
@@ -384,7 +423,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const Slice sk = slice_of(K, rank, CS);
       const int K4 = m_up4(sk.w);
       stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
       float* dst = i > 0 ? ws + J.ws_g[pp] : ws + J.ws_dzs;
       tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
       __syncthreads();
@@ -396,11 +435,11 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
       __syncthreads();
       if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
     }
     // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
     load_rows(bufB, ws + J.ws_dzs, L, BP);
-    __syncthreads();
+    cp_async_wait_all(); __syncthreads();
     if (rank == 0) {
       // g_lv[l] = sum_b dzs*z1 * 0.5*s_l - 0.5*(1 - e^lv_l): one warp per l
       for (int l = tid >> 5; l < L; l += kMT / 32) {
@@ -421,12 +460,11 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
       const float* HT = xT;
       if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); HT = bufA; }
-      __syncthreads();
       if (i > 0) {
         const Slice sk = slice_of(K, rank, CS);
         const int K4 = m_up4(sk.w);
         stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
-        __syncthreads();
+        cp_async_wait_all(); __syncthreads();
         tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
         __syncthreads();
       }
@@ -437,7 +475,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
       __syncthreads();
       if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
-      __syncthreads();
+      cp_async_wait_all(); __syncthreads();
     }
     // the next step's phase-R barrier orders this step's parameter writes before any read
   }
@@ -520,6 +558,21 @@ int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o) {
 }
 
 size_t mlp_job_bytes() { return sizeof(MlpJobDev); }
+
+// clusters (= models) that can be resident at once on the current device
+int mlp_resident_jobs(size_t smem, int* out) {
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kMlpMaxCluster * 64, 1, 1);
+  cfg.blockDim = dim3(kMT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kMlpMaxCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  VAE_CUDA_OK(cudaOccupancyMaxActiveClusters(out, fused_mlp_kernel, &cfg));
+  return 0;
+}
 
 int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s) {
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -222,6 +222,13 @@ def fused_ctas_per_sm(job: VaeTrainJob) -> int:
     return n
 
 
+def fused_resident_jobs(job: VaeTrainJob) -> int:
+    n = int(_lib.load().vae_train_fused_resident_jobs(C.byref(job)))
+    if n < 0:
+        check(n, "vae_train_fused_resident_jobs")
+    return n
+
+
 def train_fused(jobs: Sequence[VaeTrainJob], n_steps: int, scratch: torch.Tensor):
     """One persistent launch: n_steps consecutive hot-loop iterations (model.py:221-222)
     for every job."""

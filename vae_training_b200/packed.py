@@ -125,6 +125,9 @@ class PackedRuns:
         self.hkeys = torch.zeros(self.M * 8, dtype=torch.uint32, pin_memory=pin)
         self.hloss = torch.zeros(self.M * self.max_chunk, dtype=torch.float32, pin_memory=pin)
         self.jobs = [self._make_job(i) for i in range(self.M)]
+        # class-2 (cluster kernel) jobs need an L2-resident exchange workspace each
+        self.workspaces = [ops.fused_workspace(j, dev) for j in self.jobs]
+        self.jobs = [self._make_job(i, self.workspaces[i]) for i in range(self.M)]
         unsupported = [i for i, j in enumerate(self.jobs) if ops.fused_supported(j) == 0]
         if unsupported:
             s = self.specs[unsupported[0]]
@@ -164,10 +167,10 @@ class PackedRuns:
     def losses(self, i, n):
         return self.loss[i * self.max_chunk:i * self.max_chunk + n]
 
-    def _make_job(self, i):
+    def _make_job(self, i, workspace=None):
         return ops.make_job(self.descs[i], self.datas[i], self.params(i), self.adam_m(i), self.adam_v(i),
                             self.step_of(i), self.model_key(i), self.dataset_key(i), self.gen_matrix(i),
-                            self.losses(i, self.max_chunk))
+                            self.losses(i, self.max_chunk), workspace=workspace)
 
     # state movement ----------------------------------------------------------
     def _stage(self, states: Sequence[HostState]):
