@@ -21,7 +21,7 @@
 
 namespace vae {
 
-constexpr int kMT = 256;                       // threads per CTA
+constexpr int kMT = 512;                       // threads per CTA
 constexpr int kML = VAE_MAX_HIDDEN + 1;        // max Dense layers per net
 constexpr int kMlpMaxCluster = 8;
 
@@ -84,8 +84,15 @@ __device__ __forceinline__ void load_rows(float* dst, const float* src, int nrow
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, const float* __restrict__ Ws, int W4,
                                           int w, const float* __restrict__ add_g, int o0, bool relu,
                                           const float* __restrict__ maskT, float* __restrict__ outT_g, int BP, int B) {
-  const int ncg = W4 >> 2, NG = BP >> 2;
-  for (int tile = threadIdx.x; tile < ncg * NG; tile += kMT) {
+  // 4x4 output tiles; the reduction over k is split between the two lanes of a pair (halves
+  // of K), combined with a shuffle: twice the warps in flight for the same instruction count.
+  const int ncg = W4 >> 2, NG = BP >> 2, ntile = ncg * NG;
+  const int kh = (K + 1) >> 1;
+  for (int tt0 = 0; tt0 < 2 * ntile; tt0 += kMT) {
+    const int tt = tt0 + (int)threadIdx.x;
+    if (tt0 + ((int)threadIdx.x & ~31) >= 2 * ntile) break;              // warp-uniform
+    const bool live = tt < 2 * ntile;
+    const int tile = live ? tt >> 1 : ntile - 1, half = tt & 1;
     const int cg = tile / NG, rg = tile - cg * NG;
     float acc[4][4];
 #pragma unroll
@@ -94,8 +101,9 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, c
       for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
     const float* ap = AT + 4 * rg;
     const float* wp = Ws + 4 * cg;
+    const int kbeg = half ? kh : 0, kend = half ? K : kh;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    for (int k = kbeg; k < kend; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(ap + k * BP);
       const float4 wv = *reinterpret_cast<const float4*>(wp + k * W4);
       const float av[4] = {a.x, a.y, a.z, a.w};
@@ -105,6 +113,11 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, c
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[j][r] = fmaf(wj[j], av[r], acc[j][r]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[j][r] += __shfl_xor_sync(0xffffffffu, acc[j][r], 1);
+    if (!live || half) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = 4 * cg + j;
@@ -432,9 +445,8 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const int W4 = m_up4(sc.w);
       if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
       cluster_barrier();
+      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
       adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
-      __syncthreads();
-      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
       cp_async_wait_all(); __syncthreads();
     }
     // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
@@ -472,9 +484,8 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const int W4 = m_up4(sc.w);
       if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
       if (i > 0) cluster_barrier(); else __syncthreads();
+      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
       adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
-      __syncthreads();
-      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
       cp_async_wait_all(); __syncthreads();
     }
     // the next step's phase-R barrier orders this step's parameter writes before any read
