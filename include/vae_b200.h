@@ -199,6 +199,25 @@ size_t vae_train_fused_scratch_bytes(int32_t n_jobs);
 int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
                     size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------- tensor-core GEMM building blocks
+ * Used by the per-op step when a Dense layer is a true dense contraction (configs[4]:
+ * width 4096, batch 65 536).  FP32-level accuracy through a 3xTF32 split; see
+ * vae_training_b200/csrc/gemm_tc.cu.  They replace the XLA dot inside flax.nn.Dense
+ * (networks.py:33-34) and its two transposes in the backward pass.
+ *
+ * hi = TF32(x), lo = TF32(x - hi), both rounded to nearest: hi + lo = x to ~2^-23. */
+int vae_split_tf32(const float* d_x, float* d_hi, float* d_lo, int64_t n, void* stream);
+/* x (rows x cols, leading dimension ldx) -> hiT, loT (cols x rows, leading dimension ldt). */
+int vae_transpose_split_tf32(const float* d_x, int64_t ldx, float* d_hiT, float* d_loT, int64_t ldt,
+                             int32_t rows, int32_t cols, void* stream);
+/* C[M,N] = epi(A[M,K] * B[N,K]^T), A = Ah + Al, B = Bh + Bl (both row-major, K contiguous;
+ * lda, ldb multiples of 4 floats, operands 16-byte aligned).  tcgen05.mma kind::tf32 with the
+ * accumulator in tensor memory, operands staged by TMA.  flags: 1 add bias[N], 2 relu,
+ * 4 multiply by (mask[M,N] > 0). */
+int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const float* d_Al, int64_t lda,
+                       const float* d_Bh, const float* d_Bl, int64_t ldb, float* d_C, int64_t ldc,
+                       const float* d_bias, const float* d_mask, int64_t ldm, int32_t flags, void* stream);
+
 /* ----------------------------------------------------------------------- misc */
 const char* vae_last_error(void);
 int vae_abi_version(void);

@@ -71,6 +71,10 @@ _PROTOTYPES = {
     "vae_train_fused_resident_jobs": (C.c_int, [C.POINTER(VaeTrainJob)]),
     "vae_train_fused_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "vae_train_fused": (C.c_int, [C.POINTER(VaeTrainJob), C.c_int32, C.c_int64, _P, C.c_size_t, _P]),
+    "vae_split_tf32": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "vae_transpose_split_tf32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "vae_gemm_nt_3xtf32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_int64, _P,
+                                     C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
     "vae_last_error": (C.c_char_p, []),
     "vae_abi_version": (C.c_int, []),
     "vae_ffma_probe": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _P]),

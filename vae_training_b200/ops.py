@@ -243,6 +243,36 @@ def fused_scratch(n_jobs: int, device="cuda") -> torch.Tensor:
     return torch.empty((max(need, 16),), dtype=torch.uint8, device=device)
 
 
+# ------------------------------------------------------------ tensor-core building blocks
+
+def split_tf32(x: torch.Tensor):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.load().vae_split_tf32(_ptr(x, torch.float32, "x"), _ptr(hi), _ptr(lo), x.numel(), _stream()), "vae_split_tf32")
+    return hi, lo
+
+
+def transpose_split_tf32(x: torch.Tensor):
+    rows, cols = x.shape
+    hi = torch.empty((cols, rows), dtype=torch.float32, device=x.device)
+    lo = torch.empty_like(hi)
+    check(_lib.load().vae_transpose_split_tf32(_ptr(x, torch.float32, "x"), cols, _ptr(hi), _ptr(lo), rows, rows, cols,
+                                               _stream()), "vae_transpose_split_tf32")
+    return hi, lo
+
+
+def gemm_nt_3xtf32(Ah, Al, Bh, Bl, bias=None, relu=False, mask=None, out=None) -> torch.Tensor:
+    """C[M,N] = epi((Ah+Al)[M,K] @ (Bh+Bl)[N,K]^T) on the tensor cores (3xTF32)."""
+    M, K = Ah.shape
+    N = Bh.shape[0]
+    C_ = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=Ah.device)
+    flags = (1 if bias is not None else 0) | (2 if relu else 0) | (4 if mask is not None else 0)
+    check(_lib.load().vae_gemm_nt_3xtf32(M, N, K, _ptr(Ah, torch.float32, "Ah"), _ptr(Al, torch.float32, "Al"), K,
+                                         _ptr(Bh, torch.float32, "Bh"), _ptr(Bl, torch.float32, "Bl"), K, _ptr(C_), N,
+                                         _ptr(bias, torch.float32, "bias"), _ptr(mask, torch.float32, "mask"), N, flags,
+                                         _stream()), "vae_gemm_nt_3xtf32")
+    return C_
+
+
 def ffma_probe(blocks: int, threads: int, iters: int, sink: torch.Tensor) -> float:
     flops = C.c_double(0.0)
     check(_lib.load().vae_ffma_probe(_ptr(sink, torch.float32, "sink"), blocks, threads, iters, C.byref(flops),
