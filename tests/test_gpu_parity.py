@@ -154,6 +154,8 @@ STEP_CASES = {
     "sphere_21_16_h200": vs.VaeDesc(100, 21, 16, [200, 200, 200], [200, 200, 200], epsilon0=-3.0),
     "fixed_var_ragged": vs.VaeDesc(37, 5, 3, [17], [9, 33], tunable_decoder_var=False, epsilon0=-0.5),
     "wide_batch": vs.VaeDesc(1000, 16, 8, [64, 48], [48, 64], epsilon0=-2.0),
+    # rows >= 1024, width >= 256, all dims % 4 == 0: Dense layers go through the tcgen05 3xTF32 GEMM
+    "tc_route": vs.VaeDesc(1024, 64, 16, [256, 320], [256, 256], epsilon0=-2.0),
 }
 
 
@@ -212,7 +214,7 @@ def test_train_steps_vs_oracle(ops, lib, name):
     assert_params_close(P.cpu().numpy(), of, 20, d.lr, frac=0.95 if d.enc_hidden else 0.99)
 
 
-@pytest.mark.parametrize("name", ["sphere_21_16_h200", "sigmoid_28_24", "wide_batch"])
+@pytest.mark.parametrize("name", ["sphere_21_16_h200", "sigmoid_28_24", "wide_batch", "tc_route"])
 def test_train_steps_well_conditioned_all_params(ops, lib, name):
     """Same as above with adam_eps = 1.0 (>> the absolute float32 gradient noise, which is
     ~1e-5 x max|g| and max|g| is O(10..100) here because 1/var_d = e^3): the m/sqrt(v)

@@ -276,8 +276,25 @@ struct Workspace {
   float* dzs;
   float* part;     // 3 * kMaxPart
   float* grad;     // n_params
+  // tensor-core route (use_tc): 3xTF32 operand staging, reused layer after layer
+  bool tc;
+  float *xh, *xl;       // split(layer input)            rows x maxw
+  float *xth, *xtl;     // transpose_split(layer input)  maxw x rows
+  float *dyh, *dyl;     // split(dY)                     rows x maxw
+  float *dyth, *dytl;   // transpose_split(dY)           maxw x rows
+  float *wh, *wl;       // split(W) / transpose_split(W) maxw x maxw
   size_t bytes;
 };
+
+// Dense layers are routed to the tcgen05 3xTF32 GEMM (gemm_tc.cu) when they are true dense
+// contractions: many rows, wide layers, and every dimension a multiple of 4 floats (TMA
+// strides).  Everything else stays on the FP32 FFMA tiles above.
+static bool use_tc(const Layout& L, int rows) {
+  if (rows < 1024 || rows % 4 != 0 || L.max_width < 256) return false;
+  for (int i = 0; i <= L.n_enc; ++i) if (L.enc_sizes[i] % 4) return false;
+  for (int i = 0; i <= L.n_dec; ++i) if (L.dec_sizes[i] % 4) return false;
+  return true;
+}
 constexpr int kMaxPart = 1184;   // 148 * 8 blocks
 
 static inline size_t al(size_t n_floats) { return (n_floats * sizeof(float) + 255) & ~(size_t)255; }
@@ -296,6 +313,13 @@ static void carve(const VaeDesc* d, const Layout& L, int rows, void* base, Works
   w->dzs = take((size_t)rows * d->latent_dim);
   w->part = take(3 * kMaxPart);
   w->grad = take((size_t)L.n_params);
+  w->tc = use_tc(L, rows);
+  if (w->tc) {
+    const size_t act = (size_t)rows * L.max_width, ww = (size_t)L.max_width * L.max_width;
+    w->xh = take(act); w->xl = take(act); w->xth = take(act); w->xtl = take(act);
+    w->dyh = take(act); w->dyl = take(act); w->dyth = take(act); w->dytl = take(act);
+    w->wh = take(ww); w->wl = take(ww);
+  }
   w->bytes = off;
 }
 
@@ -309,11 +333,23 @@ static inline int ew_grid(int64_t total) {
 // Forward MLP: acts[i] = relu?(in_i W_i + b_i)   (networks.py:28-39)
 static int mlp_forward(cudaStream_t s, const float* params, const int* sizes, int n_layers,
                        const int64_t* w_off, const int64_t* b_off, const float* input, int rows,
-                       float* const* acts) {
+                       float* const* acts, const Workspace* tcw = nullptr) {
   const float* h = input;
   for (int i = 0; i < n_layers; ++i) {
     const int in = sizes[i], out = sizes[i + 1];
     const int flags = GEMM_BIAS | (i + 1 < n_layers ? GEMM_RELU : 0);
+    if (tcw && tcw->tc) {
+      // Y = X W + b as C[rows,out] = X[rows,in] * (W^T)[out,in]^T on the tensor cores
+      int rc = vae_split_tf32(h, tcw->xh, tcw->xl, (int64_t)rows * in, s);
+      if (rc) return rc;
+      rc = vae_transpose_split_tf32(params + w_off[i], out, tcw->wh, tcw->wl, in, in, out, s);
+      if (rc) return rc;
+      rc = vae_gemm_nt_3xtf32(rows, out, in, tcw->xh, tcw->xl, in, tcw->wh, tcw->wl, in, acts[i], out,
+                              params + b_off[i], nullptr, 0, 1 | (i + 1 < n_layers ? 2 : 0), s);
+      if (rc) return rc;
+      h = acts[i];
+      continue;
+    }
     int rc = gemm(s, rows, out, in, h, in, 1, params + w_off[i], out, 1, acts[i], out,
                   params + b_off[i], nullptr, 0, flags);
     if (rc) return rc;
@@ -327,11 +363,35 @@ static int mlp_forward(cudaStream_t s, const float* params, const int* sizes, in
 static int mlp_backward(cudaStream_t s, const float* params, float* grad, const int* sizes, int n_layers,
                         const int64_t* w_off, const int64_t* b_off, const float* input,
                         float* const* acts, int rows, const float* dout, float* ga, float* gb,
-                        float* d_in, bool need_dx, bool acc_dx) {
+                        float* d_in, bool need_dx, bool acc_dx, const Workspace* tcw = nullptr) {
   const float* d = dout;
   for (int i = n_layers - 1; i >= 0; --i) {
     const int in = sizes[i], out = sizes[i + 1];
     const float* h_in = i == 0 ? input : acts[i - 1];
+    if (tcw && tcw->tc && !acc_dx) {
+      // dW[in,out] = (X^T)[in,rows] * (dY^T)[out,rows]^T ; dX[rows,in] = dY[rows,out] * W[in,out]^T
+      int rc = vae_transpose_split_tf32(h_in, in, tcw->xth, tcw->xtl, rows, rows, in, s);
+      if (rc) return rc;
+      rc = vae_transpose_split_tf32(d, out, tcw->dyth, tcw->dytl, rows, rows, out, s);
+      if (rc) return rc;
+      rc = vae_gemm_nt_3xtf32(in, out, rows, tcw->xth, tcw->xtl, rows, tcw->dyth, tcw->dytl, rows, grad + w_off[i], out,
+                              nullptr, nullptr, 0, 0, s);
+      if (rc) return rc;
+      colsum_kernel<<<(out + 31) / 32, 256, 0, s>>>(d, out, nullptr, 0, rows, out, grad + b_off[i]);
+      VAE_LAUNCH_OK("colsum_kernel");
+      if (i > 0 || need_dx) {
+        rc = vae_split_tf32(d, tcw->dyh, tcw->dyl, (int64_t)rows * out, s);
+        if (rc) return rc;
+        rc = vae_split_tf32(params + w_off[i], tcw->wh, tcw->wl, (int64_t)in * out, s);
+        if (rc) return rc;
+        float* dst = i > 0 ? ((d == ga) ? gb : ga) : d_in;
+        rc = vae_gemm_nt_3xtf32(rows, in, out, tcw->dyh, tcw->dyl, out, tcw->wh, tcw->wl, out, dst, in, nullptr,
+                                i > 0 ? h_in : nullptr, in, i > 0 ? 4 : 0, s);
+        if (rc) return rc;
+        d = dst;
+      }
+      continue;
+    }
     // dW = h_in^T d
     int rc = gemm(s, in, out, rows, h_in, 1, in, d, out, 1, grad + w_off[i], out, nullptr, nullptr, 0, 0);
     if (rc) return rc;
@@ -383,13 +443,13 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
 
   float* mu = w.enc_act[L.n_enc - 1];
   if (mode != MODE_SAMPLE) {
-    rc = mlp_forward(s, params, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, rows, w.enc_act);
+    rc = mlp_forward(s, params, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, rows, w.enc_act, &w);
     if (rc) return rc;
   }
   const int g_lat = ew_grid((int64_t)rows * Ld);
   reparam_kernel<<<g_lat, 256, 0, s>>>(mu, d_z, ldz, lv, rows, Ld, mode == MODE_SAMPLE, w.zs, part_mu2);
   VAE_LAUNCH_OK("reparam_kernel");
-  rc = mlp_forward(s, params, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, rows, w.dec_act);
+  rc = mlp_forward(s, params, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, rows, w.dec_act, &w);
   if (rc) return rc;
   float* sig_out = nullptr;
   if (desc->sig_decoder) {
@@ -412,7 +472,7 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
 
   // backward: decoder(s) -> dzs
   rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, w.dec_act, rows,
-                    w.dxhat, w.ga, w.gb, w.dzs, true, false);
+                    w.dxhat, w.ga, w.gb, w.dzs, true, false, &w);
   if (rc) return rc;
   if (desc->sig_decoder) {
     rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.sig_w, L.sig_b, w.zs, w.sig_act, rows,
@@ -424,7 +484,7 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   latent_grad_kernel<<<g_lat, 256, 0, s>>>(w.dzs, mu, lv, rows, Ld, inv_bs, grad + L.off_eps_p);
   VAE_LAUNCH_OK("latent_grad_kernel");
   rc = mlp_backward(s, params, grad, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, w.enc_act, rows,
-                    w.dzs, w.ga, w.gb, nullptr, false, false);
+                    w.dzs, w.ga, w.gb, nullptr, false, false, &w);
   return rc;
 }
 
