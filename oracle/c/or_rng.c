@@ -1,5 +1,5 @@
 /* ORACLE (test infrastructure) -- see vae_oracle.h.  Compiled with -ffp-contract=off:
- * every float operation here is a single IEEE binary32 op in the exact order of
+ * every float operation here is a single IEEE binary32 op (or an explicit fmaf) in the exact order of
  * oracle/jax_random.py and oracle/datasets.py, so results are bit-identical to them.
  *
  * Restates third-party jax.random (un-vendored, un-pinned; README.md:8-13) as used at
@@ -61,23 +61,23 @@ static inline float neg_log1p_neg(float t) {
   k += big;
   const float m = u2f(mb);
   const float inv_scale = u2f((uint32_t)(127 - k) << 23);
-  const float f = (m - 1.0f) + c * inv_scale;
+  const float f = fmaf(c, inv_scale, m - 1.0f);
   const float fk = (float)k;
   const float z = f * f;
   float p = 7.0376836292e-2f;
-  p = p * f + -1.1514610310e-1f;
-  p = p * f + 1.1676998740e-1f;
-  p = p * f + -1.2420140846e-1f;
-  p = p * f + 1.4249322787e-1f;
-  p = p * f + -1.6668057665e-1f;
-  p = p * f + 2.0000714765e-1f;
-  p = p * f + -2.4999993993e-1f;
-  p = p * f + 3.3333331174e-1f;
+  p = fmaf(p, f, -1.1514610310e-1f);
+  p = fmaf(p, f, 1.1676998740e-1f);
+  p = fmaf(p, f, -1.2420140846e-1f);
+  p = fmaf(p, f, 1.4249322787e-1f);
+  p = fmaf(p, f, -1.6668057665e-1f);
+  p = fmaf(p, f, 2.0000714765e-1f);
+  p = fmaf(p, f, -2.4999993993e-1f);
+  p = fmaf(p, f, 3.3333331174e-1f);
   float y = (p * f) * z;
-  y = y + fk * -2.12194440e-4f;
-  y = y - 0.5f * z;
+  y = fmaf(fk, -2.12194440e-4f, y);
+  y = fmaf(-0.5f, z, y);
   float r = f + y;
-  r = r + fk * 0.693359375f;
+  r = fmaf(fk, 0.693359375f, r);
   return -r;
 }
 
@@ -92,7 +92,7 @@ static inline float erf_inv(float u) {
   const float ww = central ? w - 2.5f : sqrtf(w) - 3.0f;
   const float* c = central ? ERFINV_C : ERFINV_T;
   float p = c[0];
-  for (int i = 1; i < 9; ++i) p = p * ww + c[i];
+  for (int i = 1; i < 9; ++i) p = fmaf(p, ww, c[i]);
   return p * u;
 }
 

@@ -2,8 +2,8 @@
 //
 // RNG restates jax.random's legacy threefry2x32 path (call sites: model.py:227,
 // vae.py:56,125, datasets.py:51,76,185,242 in the reference).  Every float op on the
-// normal() path is an explicitly rounded __f*_rn intrinsic so ptxas cannot contract
-// it into an FMA: results are bit-identical to oracle/jax_random.py.
+// normal() path is an explicitly rounded __f*_rn intrinsic (fused exactly where the oracle
+// fuses, never by ptxas' choice): results are bit-identical to oracle/jax_random.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -110,40 +110,40 @@ __device__ __forceinline__ float neg_log1p_neg(float t) {
   k += big ? 1 : 0;
   const float m = __uint_as_float(mb);
   const float inv_scale = __uint_as_float((uint32_t)(127 - k) << 23);
-  const float f = __fadd_rn(__fsub_rn(m, 1.0f), __fmul_rn(c, inv_scale));
+  const float f = __fmaf_rn(c, inv_scale, __fsub_rn(m, 1.0f));
   const float fk = (float)k;
   const float z = __fmul_rn(f, f);
   float p = 7.0376836292e-2f;
-  p = __fadd_rn(__fmul_rn(p, f), -1.1514610310e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), 1.1676998740e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), -1.2420140846e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), 1.4249322787e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), -1.6668057665e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), 2.0000714765e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), -2.4999993993e-1f);
-  p = __fadd_rn(__fmul_rn(p, f), 3.3333331174e-1f);
+  p = __fmaf_rn(p, f, -1.1514610310e-1f);
+  p = __fmaf_rn(p, f, 1.1676998740e-1f);
+  p = __fmaf_rn(p, f, -1.2420140846e-1f);
+  p = __fmaf_rn(p, f, 1.4249322787e-1f);
+  p = __fmaf_rn(p, f, -1.6668057665e-1f);
+  p = __fmaf_rn(p, f, 2.0000714765e-1f);
+  p = __fmaf_rn(p, f, -2.4999993993e-1f);
+  p = __fmaf_rn(p, f, 3.3333331174e-1f);
   float y = __fmul_rn(__fmul_rn(p, f), z);
-  y = __fadd_rn(y, __fmul_rn(fk, -2.12194440e-4f));
-  y = __fsub_rn(y, __fmul_rn(0.5f, z));
+  y = __fmaf_rn(fk, -2.12194440e-4f, y);
+  y = __fmaf_rn(-0.5f, z, y);
   float r = __fadd_rn(f, y);
-  r = __fadd_rn(r, __fmul_rn(fk, 0.693359375f));
+  r = __fmaf_rn(fk, 0.693359375f, r);
   return -r;
 }
 
-// Giles single-precision erf_inv (XLA ErfInv32), unfused Horner.
+// Giles single-precision erf_inv (XLA ErfInv32), fused Horner steps (see oracle/jax_random.py).
 __device__ __forceinline__ float erf_inv_f32(float u) {
   const float w = neg_log1p_neg(__fmul_rn(u, u));
   const bool central = w < 5.0f;
   const float ww = central ? __fsub_rn(w, 2.5f) : __fsub_rn(__fsqrt_rn(w), 3.0f);
   float p = central ? 2.81022636e-08f : -0.000200214257f;
-  p = __fadd_rn(__fmul_rn(p, ww), central ? 3.43273939e-07f : 0.000100950558f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? -3.5233877e-06f : 0.00134934322f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? -4.39150654e-06f : -0.00367342844f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? 0.00021858087f : 0.00573950773f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00125372503f : -0.0076224613f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00417768164f : 0.00943887047f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? 0.246640727f : 1.00167406f);
-  p = __fadd_rn(__fmul_rn(p, ww), central ? 1.50140941f : 2.83297682f);
+  p = __fmaf_rn(p, ww, central ? 3.43273939e-07f : 0.000100950558f);
+  p = __fmaf_rn(p, ww, central ? -3.5233877e-06f : 0.00134934322f);
+  p = __fmaf_rn(p, ww, central ? -4.39150654e-06f : -0.00367342844f);
+  p = __fmaf_rn(p, ww, central ? 0.00021858087f : 0.00573950773f);
+  p = __fmaf_rn(p, ww, central ? -0.00125372503f : -0.0076224613f);
+  p = __fmaf_rn(p, ww, central ? -0.00417768164f : 0.00943887047f);
+  p = __fmaf_rn(p, ww, central ? 0.246640727f : 1.00167406f);
+  p = __fmaf_rn(p, ww, central ? 1.50140941f : 2.83297682f);
   return __fmul_rn(p, u);
 }
 
@@ -167,26 +167,26 @@ __device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
   if (__all_sync(__activemask(), w < 5.0f)) {
     const float ww = __fsub_rn(w, 2.5f);
     p = 2.81022636e-08f;
-    p = __fadd_rn(__fmul_rn(p, ww), 3.43273939e-07f);
-    p = __fadd_rn(__fmul_rn(p, ww), -3.5233877e-06f);
-    p = __fadd_rn(__fmul_rn(p, ww), -4.39150654e-06f);
-    p = __fadd_rn(__fmul_rn(p, ww), 0.00021858087f);
-    p = __fadd_rn(__fmul_rn(p, ww), -0.00125372503f);
-    p = __fadd_rn(__fmul_rn(p, ww), -0.00417768164f);
-    p = __fadd_rn(__fmul_rn(p, ww), 0.246640727f);
-    p = __fadd_rn(__fmul_rn(p, ww), 1.50140941f);
+    p = __fmaf_rn(p, ww, 3.43273939e-07f);
+    p = __fmaf_rn(p, ww, -3.5233877e-06f);
+    p = __fmaf_rn(p, ww, -4.39150654e-06f);
+    p = __fmaf_rn(p, ww, 0.00021858087f);
+    p = __fmaf_rn(p, ww, -0.00125372503f);
+    p = __fmaf_rn(p, ww, -0.00417768164f);
+    p = __fmaf_rn(p, ww, 0.246640727f);
+    p = __fmaf_rn(p, ww, 1.50140941f);
   } else {
     const bool central = w < 5.0f;
     const float ww = central ? __fsub_rn(w, 2.5f) : __fsub_rn(__fsqrt_rn(w), 3.0f);
     p = central ? 2.81022636e-08f : -0.000200214257f;
-    p = __fadd_rn(__fmul_rn(p, ww), central ? 3.43273939e-07f : 0.000100950558f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? -3.5233877e-06f : 0.00134934322f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? -4.39150654e-06f : -0.00367342844f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? 0.00021858087f : 0.00573950773f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00125372503f : -0.0076224613f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? -0.00417768164f : 0.00943887047f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? 0.246640727f : 1.00167406f);
-    p = __fadd_rn(__fmul_rn(p, ww), central ? 1.50140941f : 2.83297682f);
+    p = __fmaf_rn(p, ww, central ? 3.43273939e-07f : 0.000100950558f);
+    p = __fmaf_rn(p, ww, central ? -3.5233877e-06f : 0.00134934322f);
+    p = __fmaf_rn(p, ww, central ? -4.39150654e-06f : -0.00367342844f);
+    p = __fmaf_rn(p, ww, central ? 0.00021858087f : 0.00573950773f);
+    p = __fmaf_rn(p, ww, central ? -0.00125372503f : -0.0076224613f);
+    p = __fmaf_rn(p, ww, central ? -0.00417768164f : 0.00943887047f);
+    p = __fmaf_rn(p, ww, central ? 0.246640727f : 1.00167406f);
+    p = __fmaf_rn(p, ww, central ? 1.50140941f : 2.83297682f);
   }
   return __fmul_rn(1.41421354f, __fmul_rn(p, u));
 }

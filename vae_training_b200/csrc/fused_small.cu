@@ -207,7 +207,6 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
   const float invB = 1.0f / (float)B;
   const int half_e = (B * LD + 1) >> 1, n_e = B * LD;
   const int half_d = (B * G + 1) >> 1, n_d = B * G;
-  const int n_blocks = half_e + half_d;
 
   for (int64_t s = 0; s < n_steps; ++s) {
     const int slot = (int)(s & 1);
@@ -216,41 +215,27 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
       const uint32_t lk0 = keys[slot * 4 + 0], lk1 = keys[slot * 4 + 1];
       const uint32_t bk0 = keys[slot * 4 + 2], bk1 = keys[slot * 4 + 3];
       if (t < 4 && s + 1 < n_steps) advance_keys(slot ^ 1);
-      float* z = sm + y.z; float* gn = sm + y.gn;
-      // flat element index -> offset in the row-padded array (divisions by constants)
-      auto off_of = [](bool eps, int j) -> int {
-        const int oe = C::SZ == LD ? j : (j / LD) * C::SZ + j % LD;
-        const int od = C::SG == G ? j : (j / G) * C::SG + j % G;
-        return eps ? oe : od;
-      };
-      for (int w0 = t; w0 < n_blocks; w0 += 2 * kT) {
-        uint32_t xa[2], xb[2];
-        int ja[2], jb[2];          // element indices (negative: no store)
-        float* dst[2]; bool iseps[2];
-        uint32_t ka[2], kb[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int w = w0 + u * kT;
-          const bool valid = w < n_blocks;
-          const bool eps = w < half_e;
-          const int j = eps ? w : w - half_e;
-          const int half = eps ? half_e : half_d;
-          const int n = eps ? n_e : n_d;
-          ka[u] = eps ? lk0 : bk0; kb[u] = eps ? lk1 : bk1;
-          dst[u] = eps ? z : gn; iseps[u] = eps;
-          xa[u] = (uint32_t)j;
-          xb[u] = (j + half < n) ? (uint32_t)(j + half) : 0u;
-          ja[u] = valid ? j : -1;
-          jb[u] = (valid && j + half < n) ? j + half : -1;
+      // Two independent threefry blocks in flight per iteration; eps and generator draws are
+      // separate loops so keys / extents / destinations are loop constants.
+      auto draw = [&](const uint32_t k0, const uint32_t k1, const int half, const int n, float* dst, auto off_of) {
+        for (int w0 = t; w0 < half; w0 += 2 * kT) {
+          const int ja = w0, jb = w0 + kT;
+          const bool vb = jb < half;
+          uint32_t a0 = (uint32_t)ja, a1 = ja + half < n ? (uint32_t)(ja + half) : 0u;
+          uint32_t b0 = vb ? (uint32_t)jb : 0u, b1 = (vb && jb + half < n) ? (uint32_t)(jb + half) : 0u;
+          threefry2x32_x2(k0, k1, a0, a1, k0, k1, b0, b1);
+          const float n0 = normal_from_bits_fast(a0), n1 = normal_from_bits_fast(a1);
+          const float n2 = normal_from_bits_fast(b0), n3 = normal_from_bits_fast(b1);
+          dst[off_of(ja)] = n0;
+          if (ja + half < n) dst[off_of(ja + half)] = n1;
+          if (vb) {
+            dst[off_of(jb)] = n2;
+            if (jb + half < n) dst[off_of(jb + half)] = n3;
+          }
         }
-        threefry2x32_x2(ka[0], kb[0], xa[0], xb[0], ka[1], kb[1], xa[1], xb[1]);
-        const float n0 = normal_from_bits_fast(xa[0]), n1 = normal_from_bits_fast(xb[0]);
-        const float n2 = normal_from_bits_fast(xa[1]), n3 = normal_from_bits_fast(xb[1]);
-        if (ja[0] >= 0) dst[0][off_of(iseps[0], ja[0])] = n0;
-        if (jb[0] >= 0) dst[0][off_of(iseps[0], jb[0])] = n1;
-        if (ja[1] >= 0) dst[1][off_of(iseps[1], ja[1])] = n2;
-        if (jb[1] >= 0) dst[1][off_of(iseps[1], jb[1])] = n3;
-      }
+      };
+      draw(lk0, lk1, half_e, n_e, sm + y.z, [](int j) { return C::SZ == LD ? j : (j / LD) * C::SZ + j % LD; });
+      draw(bk0, bk1, half_d, n_d, sm + y.gn, [](int j) { return C::SG == G ? j : (j / G) * C::SG + j % G; });
     }
     __syncthreads();
     // ================= phase B: one thread per batch row
