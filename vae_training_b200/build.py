@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2",
-] + (["-DVAE_FUSED_DEBUG"] if os.environ.get("VAE_FUSED_DEBUG") else [])
+] + ([f"-DVAE_SMALL_MAXB={os.environ['VAE_SMALL_MAXB']}"] if os.environ.get("VAE_SMALL_MAXB") else [])
 
 
 def find_nvcc() -> str:

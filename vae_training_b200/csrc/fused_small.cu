@@ -29,7 +29,7 @@ namespace vae {
 
 constexpr int kT = 128;
 #ifndef VAE_SMALL_MAXB
-#define VAE_SMALL_MAXB 6
+#define VAE_SMALL_MAXB 8
 #endif
 
 struct FusedJobDev {
@@ -215,11 +215,23 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
       const uint32_t lk0 = keys[slot * 4 + 0], lk1 = keys[slot * 4 + 1];
       const uint32_t bk0 = keys[slot * 4 + 2], bk1 = keys[slot * 4 + 3];
       if (t < 4 && s + 1 < n_steps) advance_keys(slot ^ 1);
-      // Two independent threefry blocks in flight per iteration; eps and generator draws are
-      // separate loops so keys / extents / destinations are loop constants.
-      auto draw = [&](const uint32_t k0, const uint32_t k1, const int half, const int n, float* dst, auto off_of) {
-        for (int w0 = t; w0 < half; w0 += 2 * kT) {
-          const int ja = w0, jb = w0 + kT;
+      // Two passes over ONE loop body (eps draw, generator draw): keys / extents / destination
+      // are pass constants, and each thread-iteration owns an adjacent pair of threefry blocks
+      // (two independent chains in flight).
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t k0 = pass ? bk0 : lk0, k1 = pass ? bk1 : lk1;
+        const int half = pass ? half_d : half_e, n = pass ? n_d : n_e;
+        float* dst = sm + (pass ? y.gn : y.z);
+        auto off_of = [&](int j) -> int {
+          const int oe = C::SZ == LD ? j : (j / LD) * C::SZ + j % LD;
+          const int od = C::SG == G ? j : (j / G) * C::SG + j % G;
+          return pass ? od : oe;
+        };
+        const int npair = (half + 1) >> 1;
+#pragma unroll 1
+        for (int pi = t; pi < npair; pi += kT) {
+          const int ja = 2 * pi, jb = 2 * pi + 1;
           const bool vb = jb < half;
           uint32_t a0 = (uint32_t)ja, a1 = ja + half < n ? (uint32_t)(ja + half) : 0u;
           uint32_t b0 = vb ? (uint32_t)jb : 0u, b1 = (vb && jb + half < n) ? (uint32_t)(jb + half) : 0u;
@@ -233,9 +245,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
             if (jb + half < n) dst[off_of(jb + half)] = n3;
           }
         }
-      };
-      draw(lk0, lk1, half_e, n_e, sm + y.z, [](int j) { return C::SZ == LD ? j : (j / LD) * C::SZ + j % LD; });
-      draw(bk0, bk1, half_d, n_d, sm + y.gn, [](int j) { return C::SG == G ? j : (j / G) * C::SG + j % G; });
+      }
     }
     __syncthreads();
     // ================= phase B: one thread per batch row
