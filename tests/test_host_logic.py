@@ -100,3 +100,28 @@ def test_make_output_dir_rules(tmp_path):
     open(os.path.join(d, "junk"), "w").close()
     run.make_output_dir("exp1", True, a, data_dir=str(tmp_path))
     assert sorted(os.listdir(d)) == ["args.json"]
+
+
+def test_builtin_sweeps_match_reference_scripts():
+    """sweeps.py regenerates the three .sh files: 21 + 18 + 15 runs with the same flags.  When
+    the reference tree is present (this container) the regenerated argument namespaces are
+    compared with the parsed scripts run by run."""
+    from vae_training_b200 import sweeps
+    assert (len(sweeps.linear_runs()), len(sweeps.sigmoid_runs()), len(sweeps.sphere_runs())) == (21, 18, 15)
+    runs = sweep.builtin_runs("all")
+    assert len(runs) == 54 and sum(r.num_batches for r in runs) == 7_050_000
+    ref_dir = "/root/reference"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not available")
+    key = lambda a: (a.dataset, a.dataset_dimension, a.padding_dim, a.latent_dimension, a.dataset_seed)
+    fields = ("dataset", "dataset_dimension", "padding_dim", "latent_dimension", "dataset_seed", "num_batches",
+              "learning_rate", "epsilon", "tunable_decoder_var", "layer_sizes", "encoder_layer_sizes", "batch_size",
+              "overwrite")
+    for which, fn in (("linear", "seed_linpadding_expts.sh"), ("sigmoid", "sigmoid_vae_padding_expts.sh"),
+                      ("sphere", "sphere_vae_padding_expts.sh")):
+        ref = {key(a): a for a in sweep.parse_script(os.path.join(ref_dir, fn))}
+        mine = {key(a): a for a in sweep.builtin_runs(which)}
+        assert set(ref) == set(mine), which
+        for k in ref:
+            for f in fields:
+                assert getattr(ref[k], f) == getattr(mine[k], f), (which, k, f)

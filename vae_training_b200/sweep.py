@@ -4,6 +4,7 @@ or an LPT partition of them when launched under torchrun (one process per GPU, n
 communication -- the runs are independent).
 
     python -m vae_training_b200.sweep seed_linpadding_expts.sh sigmoid_vae_padding_expts.sh ...
+    python -m vae_training_b200.sweep builtin:all          # the 54 runs, regenerated from their grids
 """
 from __future__ import annotations
 
@@ -63,11 +64,32 @@ def run_sweep(all_args, rank=0, world=1, save=True, verbose=False):
     return models
 
 
+def builtin_runs(which: str, num_batches=None) -> List:
+    """The reference's sweeps regenerated from their grids (sweeps.py); `which` in
+    linear | sigmoid | sphere | all.  num_batches overrides the run length (smoke tests)."""
+    from . import sweeps
+    out = []
+    for argv in sweeps.BUILTIN[which]():
+        a = runmod.parse_arguments(argv)
+        if num_batches is not None:
+            a.num_batches = int(num_batches)
+        out.append(a)
+    return out
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     all_args = []
+    num_batches = None
+    if "--num_batches" in argv:
+        i = argv.index("--num_batches")
+        num_batches = int(argv[i + 1])
+        argv = argv[:i] + argv[i + 2:]
     for path in argv:
-        all_args += parse_script(path)
+        if path.startswith("builtin:"):
+            all_args += builtin_runs(path.split(":", 1)[1], num_batches)
+        else:
+            all_args += parse_script(path)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if "LOCAL_RANK" in os.environ:
