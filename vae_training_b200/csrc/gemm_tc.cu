@@ -21,6 +21,7 @@
 //   warps 2-5   drain + epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quarter),
 //               two-level accumulation (see below), fused bias / relu / relu-mask, float4 stores
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -57,6 +58,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+// Multicast variant: the box lands at the same smem offset (and signals the mbarrier at the same
+// offset) in every CTA of the cluster named by cta_mask.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -105,6 +120,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MC = 2: clusters of two CTAs that are neighbours along M share their B tiles -- each CTA
+// fetches half of Bh / Bl (64 rows) and TMA-multicasts it into both CTAs' shared memory, which
+// cuts the L2 -> SM operand traffic per CTA from 64 KB to 48 KB per k-block (the kernel is
+// L2-bandwidth bound: ncu shows 13 TB/s of xbar reads at 62 % tensor-pipe activity for MC = 1).
+// A stage may be refilled only when BOTH CTAs' MMAs have consumed it: tcgen05.commit arrives on
+// the empty barrier of both CTAs (count 2).
+template <int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -122,6 +144,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int nchunk = (nkb + TC_CHUNK - 1) / TC_CHUNK;
+  const uint32_t crank = MC > 1 ? tc_cluster_ctarank() : 0u;       // position along M inside the cluster
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAh)));
@@ -130,7 +153,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)));
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC); }
     for (int b = 0; b < 2; ++b) { mbar_init(&mfull_bar[b], 1); mbar_init(&mempty_bar[b], 4); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,6 +164,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) tc_cluster_sync();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
   const uint32_t tmem_small = tmem_acc + 2 * TC_BN;
@@ -156,8 +180,15 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
         tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
         tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
-        tma_load_2d(st + 2 * TC_TILE_BYTES, &tmBh, &full_bar[s], kb * TC_BK, n0);
-        tma_load_2d(st + 3 * TC_TILE_BYTES, &tmBl, &full_bar[s], kb * TC_BK, n0);
+        if (MC == 1) {
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &tmBh, &full_bar[s], kb * TC_BK, n0);
+          tma_load_2d(st + 3 * TC_TILE_BYTES, &tmBl, &full_bar[s], kb * TC_BK, n0);
+        } else {      // this CTA's half of the B rows, multicast to both CTAs of the cluster
+          const int half_rows = TC_BN / MC;
+          const size_t off = (size_t)crank * half_rows * TC_BK * 4;
+          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)crank * half_rows, (uint16_t)((1u << MC) - 1));
+          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)crank * half_rows, (uint16_t)((1u << MC) - 1));
+        }
       }
     }
   } else if (warp == 1) {
@@ -186,7 +217,8 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           umma_tf32(tmem_small, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
           umma_tf32(tmem_small, dAl + adv, dBh + adv, idesc, 1u);
         }
-        umma_commit(&empty_bar[s]);                        // smem slot reusable once these MMAs retire
+        if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
+        else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
         if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) umma_commit(&mfull_bar[buf]);
       }
       umma_commit(&acc_bar);                               // every MMA of the tile complete
@@ -251,6 +283,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) tc_cluster_sync();            // no CTA leaves while its peer may still signal its barriers
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TC_TMEM_COLS));
 }
 
@@ -315,18 +348,24 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // rows x K row-major (leading dimension ld floats): boxes of 128 rows x 32 floats, SWIZZLE_128B
-static int make_operand_map(CUtensorMap* tm, const float* ptr, int rows, int K, int64_t ld) {
+static int make_operand_map(CUtensorMap* tm, const float* ptr, int rows, int K, int64_t ld, int box_rows = TC_BM) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VAE_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return VAE_ERR_CUDA; }
   return 0;
+}
+
+// VAE_TC_SINGLE_CTA=1 in the environment selects the non-multicast kernel (A/B comparison)
+static bool tc_force_single_cta() {
+  const char* e = getenv("VAE_TC_SINGLE_CTA");
+  return e && e[0] == '1';
 }
 
 }  // namespace vae
@@ -368,13 +407,30 @@ int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const
   int rc;
   if ((rc = vae::make_operand_map(&tAh, d_Ah, M, K, lda))) return rc;
   if ((rc = vae::make_operand_map(&tAl, d_Al, M, K, lda))) return rc;
-  if ((rc = vae::make_operand_map(&tBh, d_Bh, N, K, ldb))) return rc;
-  if ((rc = vae::make_operand_map(&tBl, d_Bl, N, K, ldb))) return rc;
-  VAE_CUDA_OK(cudaFuncSetAttribute(vae::gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vae::TC_SMEM_BYTES));
-  dim3 grid((N + vae::TC_BN - 1) / vae::TC_BN, (M + vae::TC_BM - 1) / vae::TC_BM);
-  vae::gemm_nt_3xtf32_kernel<<<grid, vae::TC_THREADS, vae::TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-      tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags);
-  VAE_LAUNCH_OK("gemm_nt_3xtf32_kernel");
+  const int tiles_m = (M + vae::TC_BM - 1) / vae::TC_BM, tiles_n = (N + vae::TC_BN - 1) / vae::TC_BN;
+  const int mc = (tiles_m >= 2 && !vae::tc_force_single_cta()) ? 2 : 1;
+  if ((rc = vae::make_operand_map(&tBh, d_Bh, N, K, ldb, vae::TC_BN / mc))) return rc;
+  if ((rc = vae::make_operand_map(&tBl, d_Bl, N, K, ldb, vae::TC_BN / mc))) return rc;
+  if (mc == 1) {
+    VAE_CUDA_OK(cudaFuncSetAttribute(vae::gemm_nt_3xtf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, vae::TC_SMEM_BYTES));
+    dim3 grid(tiles_n, tiles_m);
+    vae::gemm_nt_3xtf32_kernel<1><<<grid, vae::TC_THREADS, vae::TC_SMEM_BYTES, (cudaStream_t)stream>>>(
+        tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags);
+    VAE_LAUNCH_OK("gemm_nt_3xtf32_kernel<1>");
+    return 0;
+  }
+  VAE_CUDA_OK(cudaFuncSetAttribute(vae::gemm_nt_3xtf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, vae::TC_SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles_n, (tiles_m + 1) / 2 * 2, 1);      // an odd last M tile is all out-of-bounds: zero-filled loads, masked stores
+  cfg.blockDim = dim3(vae::TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = vae::TC_SMEM_BYTES;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, vae::gemm_nt_3xtf32_kernel<2>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
+                                 flags));
   return 0;
 }
 
