@@ -111,7 +111,8 @@ def test_normal_rows_matches_slice(ops, rows, cols, lo, hi):
 # -------------------------------------------------------------------- datasets
 
 DATASETS = [("sphere", 3, 3), ("sphere", 7, 7), ("linear_gaussian", 3, 9), ("linear_gaussian", 12, 8),
-            ("sigmoid", 3, 3), ("sigmoid", 7, 20), ("sphere", 5, 0)]
+            ("sigmoid", 3, 3), ("sigmoid", 7, 20), ("sphere", 5, 0),
+            ("sphere", 40, 8), ("sigmoid", 33, 3)]          # dim >= 32: the two-phase wide-row generator
 
 
 @pytest.mark.parametrize("name,dd,pd", DATASETS)
@@ -459,7 +460,8 @@ def test_normal_pairs_bit_exact(ops, rows, cols, lo, hi):
     np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("name,dd,pd", [("sphere", 5, 3), ("linear_gaussian", 6, 2), ("sigmoid", 3, 3)])
+@pytest.mark.parametrize("name,dd,pd", [("sphere", 5, 3), ("linear_gaussian", 6, 2), ("sigmoid", 3, 3), ("sphere", 64, 16),
+                                        ("sigmoid", 48, 0)])
 def test_dataset_pairs_bit_exact(ops, lib, name, dd, pd):
     from vae_training_b200 import dp
     size = 64

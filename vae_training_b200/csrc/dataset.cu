@@ -116,6 +116,90 @@ __global__ void dataset_score_kernel(VaeDataDesc d, const float* __restrict__ A,
   }
 }
 
+// ---- wide rows (configs[4]: -dd 512): the per-row transform is still sequential (bit-exact
+// op order), but the normals are drawn by a fully parallel pass straight into out[:, :dim]
+// (row pairs b / b + size/2 share a threefry block), then transformed in place.
+__global__ void wide_normals_kernel(const uint32_t* __restrict__ key, float* __restrict__ out, int width, int g,
+                                    int size, int lo, int n_lo, int pairs_layout) {
+  const uint32_t k0 = key[0], k1 = key[1];
+  const int64_t total = (int64_t)n_lo * g;            // blocks: (local low row i, column j)
+  const int64_t half = (int64_t)size * g / 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int i = (int)(t / g), j = (int)(t - (int64_t)i * g);
+    const int64_t e = (int64_t)(lo + i) * g + j;      // flat element of the low row; partner = e + half
+    uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(e + half);
+    threefry2x32(k0, k1, x0, x1);
+    const int r_lo = pairs_layout ? i : lo + i;
+    const int r_hi = pairs_layout ? n_lo + i : size / 2 + lo + i;
+    out[(int64_t)r_lo * width + j] = normal_from_bits(x0);
+    out[(int64_t)r_hi * width + j] = normal_from_bits(x1);
+  }
+}
+// 32 rows per block (256 threads).  The row reduction keeps the oracle's sequential order (one
+// thread per row walks its row left to right), but every global access is coalesced: 32x32
+// tiles go through shared memory.
+__global__ void __launch_bounds__(256)
+wide_transform_kernel(VaeDataDesc d, const float* __restrict__ A, int nrows, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  __shared__ float racc[32];
+  const int width = d.dim + d.padding_dim + (d.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  const int r0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (int c0 = 0; c0 < d.dim; c0 += 32) {
+    for (int rr = wp; rr < 32; rr += 8) {
+      const int r = r0 + rr, c = c0 + lane;
+      tile[rr][lane] = (r < nrows && c < d.dim) ? out[(int64_t)r * width + c] : 0.f;
+    }
+    __syncthreads();
+    if (wp == 0) {                                   // thread `lane` owns row r0 + lane
+      const int cmax = min(32, d.dim - c0);
+      for (int j = 0; j < cmax; ++j) {
+        const float v = tile[lane][j];
+        const float t = d.kind == VAE_DATA_SPHERE ? __fmul_rn(v, v) : __fmul_rn(v, A[c0 + j]);
+        acc = (c0 + j) == 0 ? t : __fadd_rn(acc, t);
+      }
+    }
+    __syncthreads();
+  }
+  if (wp == 0) racc[lane] = d.kind == VAE_DATA_SPHERE ? __fsqrt_rn(acc) : det_sigmoid(acc);
+  __syncthreads();
+  if (d.kind == VAE_DATA_SPHERE) {
+    for (int rr = wp; rr < 32; rr += 8) {
+      const int r = r0 + rr;
+      if (r >= nrows) continue;
+      float* row = out + (int64_t)r * width;
+      const float rad = racc[rr];
+      for (int c = lane; c < width; c += 32) row[c] = c < d.dim ? __fdiv_rn(row[c], rad) : 0.f;
+    }
+  } else {      // sigmoid: columns [0, dim) already hold z; column dim = sigmoid(z . A); zeros after
+    for (int rr = wp; rr < 32; rr += 8) {
+      const int r = r0 + rr;
+      if (r >= nrows) continue;
+      float* row = out + (int64_t)r * width;
+      for (int c = d.dim + lane; c < width; c += 32) row[c] = c == d.dim ? racc[rr] : 0.f;
+    }
+  }
+}
+// size even, kind sphere / sigmoid, dim >= 32: rows [lo, hi) + partners, either densely packed
+// (pairs_layout) or at their global positions (lo = 0, hi = size/2)
+static int wide_batch(const VaeDataDesc* d, const uint32_t* d_key, const float* d_A, int size, int lo, int hi,
+                      int pairs_layout, float* d_out, cudaStream_t s) {
+  const int n_lo = hi - lo, width = d->dim + d->padding_dim + (d->kind == VAE_DATA_SIGMOID ? 1 : 0);
+  const int64_t total = (int64_t)n_lo * d->dim;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wide_normals_kernel<<<(int)blocks, 256, 0, s>>>(d_key, d_out, width, d->dim, size, lo, n_lo, pairs_layout);
+  VAE_LAUNCH_OK("wide_normals_kernel");
+  wide_transform_kernel<<<(2 * n_lo + 31) / 32, 256, 0, s>>>(*d, d_A, 2 * n_lo, d_out);
+  VAE_LAUNCH_OK("wide_transform_kernel");
+  return 0;
+}
+static inline bool use_wide(const VaeDataDesc* d, int size) {
+  return d->kind != VAE_DATA_LINEAR_GAUSSIAN && d->dim >= 32 && size % 2 == 0 && size >= 2;
+}
+
 int check_data_desc(const VaeDataDesc* d) {
   if (!d) { set_error("data desc is NULL"); return VAE_ERR_INVALID; }
   if (d->kind < 0 || d->kind > 2) { set_error("unknown dataset kind %d", d->kind); return VAE_ERR_INVALID; }
@@ -137,6 +221,7 @@ int vae_dataset_batch(const VaeDataDesc* d, const uint32_t* d_key, const float* 
   if (size == 0) return 0;
   VAE_REQUIRE(d_out, "vae_dataset_batch: d_out is NULL");
   VAE_REQUIRE((int64_t)size * vae_data_normals_per_row(d) < (1ll << 32), "vae_dataset_batch: too many draws");
+  if (vae::use_wide(d, size)) return vae::wide_batch(d, d_key, d_A, size, 0, size / 2, 0, d_out, (cudaStream_t)stream);
   vae::dataset_batch_kernel<<<(size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d, d_key, d_A, size, d_out);
   VAE_LAUNCH_OK("dataset_batch_kernel");
   return 0;
@@ -153,6 +238,7 @@ int vae_dataset_batch_pairs(const VaeDataDesc* d, const uint32_t* d_key, const f
   if (n_lo == 0) return 0;
   VAE_REQUIRE(d_out, "vae_dataset_batch_pairs: d_out is NULL");
   VAE_REQUIRE((int64_t)size * vae_data_normals_per_row(d) < (1ll << 32), "vae_dataset_batch_pairs: too many draws");
+  if (vae::use_wide(d, size)) return vae::wide_batch(d, d_key, d_A, size, lo, hi, 1, d_out, (cudaStream_t)stream);
   vae::dataset_pairs_kernel<<<(2 * n_lo + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d, d_key, d_A, size, lo,
                                                                                       n_lo, d_out);
   VAE_LAUNCH_OK("dataset_pairs_kernel");

@@ -81,6 +81,11 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t sAm, int6
   }
 }
 
+constexpr int kColParts = 64;
+// column sums with the rows split over up to kColParts blocks when there are many rows
+static int colsum(cudaStream_t s, const float* Y, int64_t ldy, const float* Z, int64_t ldz, int rows, int n, float* out,
+                  float* scratch /* kColParts * n floats, or nullptr */);
+
 static int gemm(cudaStream_t s, int M, int N, int K, const float* A, int64_t sAm, int64_t sAk,
                 const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc,
                 const float* bias, const float* mask, int64_t ldm, int flags) {
@@ -91,15 +96,20 @@ static int gemm(cudaStream_t s, int M, int N, int K, const float* A, int64_t sAm
 }
 
 // out[j] = sum_r Y[r*ldy + j] * (Z ? Z[r*ldz + j] : 1)      (bias grads, dlogvar sums)
+// gridDim.y > 1: block y reduces its contiguous slice of the rows into out[y*n + j]
+// (deterministic two-stage reduction; the second stage is this kernel again on the partials).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ Z, int64_t ldz,
               int rows, int n, float* __restrict__ out) {
   __shared__ float sh[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int rbeg = blockIdx.y * per, rend = min(rows, rbeg + per);
+  out += (int64_t)blockIdx.y * n;
   float acc = 0.f;
   if (col < n) {
-    for (int r = ty; r < rows; r += 8) {
+    for (int r = rbeg + ty; r < rend; r += 8) {
       float v = Y[(int64_t)r * ldy + col];
       if (Z) v *= Z[(int64_t)r * ldz + col];
       acc += v;
@@ -126,6 +136,22 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
   }
   __syncthreads();
   return t;   // valid in warp 0
+}
+
+static int colsum(cudaStream_t s, const float* Y, int64_t ldy, const float* Z, int64_t ldz, int rows, int n, float* out,
+                  float* scratch) {
+  int parts = scratch ? rows / 512 : 1;
+  if (parts > kColParts) parts = kColParts;
+  if (parts <= 1) {
+    colsum_kernel<<<dim3((n + 31) / 32, 1), 256, 0, s>>>(Y, ldy, Z, ldz, rows, n, out);
+    VAE_LAUNCH_OK("colsum_kernel");
+    return 0;
+  }
+  colsum_kernel<<<dim3((n + 31) / 32, parts), 256, 0, s>>>(Y, ldy, Z, ldz, rows, n, scratch);
+  VAE_LAUNCH_OK("colsum_kernel(stage 1)");
+  colsum_kernel<<<dim3((n + 31) / 32, 1), 256, 0, s>>>(scratch, n, nullptr, 0, parts, n, out);
+  VAE_LAUNCH_OK("colsum_kernel(stage 2)");
+  return 0;
 }
 
 // zs = mu + exp(lv/2) * z1 ; partial sum of mu^2.   (networks.py:73-74, :94)
@@ -263,6 +289,10 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
   }
 }
 __global__ void step_inc_kernel(int32_t* step) { step[0] += 1; }
+__global__ void fill_ones_row_kernel(float* __restrict__ hi, float* __restrict__ lo, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { hi[i] = 1.0f; lo[i] = 0.0f; }
+}
 
 // ------------------------------------------------------------------- workspace
 struct Workspace {
@@ -275,6 +305,7 @@ struct Workspace {
   float* gb;
   float* dzs;
   float* part;     // 3 * kMaxPart
+  float* colpart;  // kColParts * max_width (two-stage column sums)
   float* grad;     // n_params
   // tensor-core route (use_tc): 3xTF32 operand staging, reused layer after layer
   bool tc;
@@ -312,11 +343,13 @@ static void carve(const VaeDesc* d, const Layout& L, int rows, void* base, Works
   w->gb = take((size_t)rows * L.max_width);
   w->dzs = take((size_t)rows * d->latent_dim);
   w->part = take(3 * kMaxPart);
+  w->colpart = take((size_t)kColParts * L.max_width);
   w->grad = take((size_t)L.n_params);
   w->tc = use_tc(L, rows);
   if (w->tc) {
     const size_t act = (size_t)rows * L.max_width, ww = (size_t)L.max_width * L.max_width;
-    w->xh = take(act); w->xl = take(act); w->xth = take(act); w->xtl = take(act);
+    w->xh = take(act); w->xl = take(act);
+    w->xth = take(act + rows); w->xtl = take(act + rows);      // + the all-ones row (bias gradient)
     w->dyh = take(act); w->dyl = take(act); w->dyth = take(act); w->dytl = take(act);
     w->wh = take(ww); w->wl = take(ww);
   }
@@ -374,11 +407,14 @@ static int mlp_backward(cudaStream_t s, const float* params, float* grad, const 
       if (rc) return rc;
       rc = vae_transpose_split_tf32(d, out, tcw->dyth, tcw->dytl, rows, rows, out, s);
       if (rc) return rc;
-      rc = vae_gemm_nt_3xtf32(in, out, rows, tcw->xth, tcw->xtl, rows, tcw->dyth, tcw->dytl, rows, grad + w_off[i], out,
+      // [X^T ; 1] (in+1 rows): the extra all-ones row makes the same GEMM produce the bias
+      // gradient, which sits right behind the kernel in the flat layout
+      if (b_off[i] != w_off[i] + (int64_t)in * out) { set_error("flat layout: bias does not follow kernel"); return VAE_ERR_INVALID; }
+      fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, s>>>(tcw->xth + (size_t)in * rows, tcw->xtl + (size_t)in * rows, rows);
+      VAE_LAUNCH_OK("fill_ones_row_kernel");
+      rc = vae_gemm_nt_3xtf32(in + 1, out, rows, tcw->xth, tcw->xtl, rows, tcw->dyth, tcw->dytl, rows, grad + w_off[i], out,
                               nullptr, nullptr, 0, 0, s);
       if (rc) return rc;
-      colsum_kernel<<<(out + 31) / 32, 256, 0, s>>>(d, out, nullptr, 0, rows, out, grad + b_off[i]);
-      VAE_LAUNCH_OK("colsum_kernel");
       if (i > 0 || need_dx) {
         rc = vae_split_tf32(d, tcw->dyh, tcw->dyl, (int64_t)rows * out, s);
         if (rc) return rc;
@@ -395,8 +431,8 @@ static int mlp_backward(cudaStream_t s, const float* params, float* grad, const 
     // dW = h_in^T d
     int rc = gemm(s, in, out, rows, h_in, 1, in, d, out, 1, grad + w_off[i], out, nullptr, nullptr, 0, 0);
     if (rc) return rc;
-    colsum_kernel<<<(out + 31) / 32, 256, 0, s>>>(d, out, nullptr, 0, rows, out, grad + b_off[i]);
-    VAE_LAUNCH_OK("colsum_kernel");
+    rc = colsum(s, d, out, nullptr, 0, rows, out, grad + b_off[i], tcw ? tcw->colpart : nullptr);
+    if (rc) return rc;
     if (i > 0) {
       float* dst = (d == ga) ? gb : ga;
       rc = gemm(s, rows, in, out, d, out, 1, params + w_off[i], 1, out, dst, in, nullptr, h_in, in, GEMM_MASK);
@@ -479,8 +515,8 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
                       sig_out, w.ga, w.gb, w.dzs, true, true);
     if (rc) return rc;
   }
-  colsum_kernel<<<(Ld + 31) / 32, 256, 0, s>>>(w.dzs, Ld, d_z, ldz, rows, Ld, grad + L.off_eps_p);
-  VAE_LAUNCH_OK("colsum_kernel(dlv)");
+  rc = colsum(s, w.dzs, Ld, d_z, ldz, rows, Ld, grad + L.off_eps_p, w.colpart);
+  if (rc) return rc;
   latent_grad_kernel<<<g_lat, 256, 0, s>>>(w.dzs, mu, lv, rows, Ld, inv_bs, grad + L.off_eps_p);
   VAE_LAUNCH_OK("latent_grad_kernel");
   rc = mlp_backward(s, params, grad, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, w.enc_act, rows,
