@@ -64,6 +64,10 @@ def parse():
     return ap.parse_args()
 
 
+def wl_hidden(workload):
+    return bool(WORKLOADS[workload][8])
+
+
 def make_specs(workload, n_models, first_index=0):
     from vae_training_b200.packed import RunSpec
     name, dd, pd, L, lr, eps0, seed0, _, hidden = WORKLOADS[workload]
@@ -207,6 +211,8 @@ def run_b200(args):
     else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
         probe = PackedRuns(make_specs(args.workload, 1), max_chunk=4)
         n_models = max(1, ops.fused_resident_jobs(probe.jobs[0]))
+        if n_models >= 8:
+            n_models -= n_models % 8      # whole CTAs of 4 models / whole cluster pairs (fused_small.cu)
         del probe
     specs = make_specs(args.workload, n_models, first_index=rank * n_models)
     runs = PackedRuns(specs, max_chunk=max(K, W))
@@ -239,23 +245,48 @@ def run_b200(args):
     ffma_tflops = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
     # ---- device-resident arm
+    runs.upload(states)
     runs.train_steps(W)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from vae_training_b200 import _lib
+    l0 = _lib.load().vae_launch_count()
     e0.record()
     runs.train_steps(K)
     e1.record()
+    launches = _lib.load().vae_launch_count() - l0
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     loss_dev = runs.loss.view(n_models, runs.max_chunk)[:, :K]
     if not bool(torch.isfinite(loss_dev).all()):
         raise SystemExit("bench.py: non-finite loss in the timed region")
+    loss_snapshot = loss_dev.clone()
     total_models = n_models * world
     value = total_models * K / (ms * 1e-3)
+
+    # ---- A/B: the same pack and steps with eps sharing off / through 2-CTA clusters instead
+    ab = {}
+    if not wl_hidden(args.workload):
+        for mode, env in (("private_eps_draw", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "1"}),
+                          ("cluster2_dsmem", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "2"})):
+            os.environ.update(env)
+            runs.upload(states)
+            runs.train_steps(W)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            runs.train_steps(K)
+            e1.record()
+            barrier()
+            ab[mode] = total_models * K / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+            for k in env:
+                del os.environ[k]
+            if not torch.equal(loss_snapshot, runs.loss.view(n_models, runs.max_chunk)[:, :K]):
+                raise SystemExit(f"bench.py: {mode} and the default launch disagree (must be bit-identical)")
 
     # ---- end-to-end arm: host state in (pinned), fused steps, losses + state out
     runs.train_host(states, W)
@@ -288,12 +319,19 @@ def run_b200(args):
                        "models_per_gpu": n_models, "data_dim": spec.data_dim, "latent_dim": spec.latent_dimension,
                        "l2_flush": "n/a: working set is SM-resident (shared memory); HBM traffic is the 4-byte "
                                    "loss store per model-step",
+                       "eps_draw": "4 models per CTA (512 threads); the models of a CTA whose carried model key is "
+                                   "equal (always, here: the reference seeds every model with PRNGKey(0), model.py:29) "
+                                   "share one threefry/normal draw of eps per step -- bit-identical to private draws "
+                                   "(checked in this run against both A/B launches, see eps_sharing_ab)",
                        "parallelism": f"independent models x{world} GPUs, no collective"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "note": "PackedRuns.train_host: pinned host state -> device, K fused steps, per-step losses + "
                             "final state -> host"},
-            "gpu_launches": 1,
+            "eps_sharing_ab": {"unit": UNIT, **ab,
+                               "note": "same pack and steps; private_eps_draw: one model per CTA, every model draws its "
+                                       "own eps; cluster2_dsmem: one model per CTA, pairs share the draw through DSMEM"},
+            "gpu_launches": int(launches),
             "roofline": {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
                          "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
                          "traffic": None,
@@ -368,10 +406,13 @@ def run_dp(args):
         clocks.start()
     losses = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from vae_training_b200 import _lib
+    l0 = _lib.load().vae_launch_count()
     e0.record()
     for _ in range(K):
         losses.append(model.train_step().clone())
     e1.record()
+    launches = _lib.load().vae_launch_count() - l0
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
@@ -416,7 +457,8 @@ def run_dp(args):
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 20,
                     "note": "inputs of a step are the two carried PRNG keys (batch and eps are generated on the device, "
                             "as in the reference); loss and keys are read back every step"},
-            "gpu_launches": None,
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "kernels of libvae_b200.so launched in the timed region (vae_launch_count); torch copy / NCCL kernels are not counted",
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf32_peak, "traffic": None,
                          "note": f"achieved = {flop_step / 1e12:.2f} algorithmic TFLOP/step / {world} GPUs / step time; "

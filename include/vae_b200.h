@@ -221,6 +221,9 @@ int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const
 /* ----------------------------------------------------------------------- misc */
 const char* vae_last_error(void);
 int vae_abi_version(void);
+/* Number of CUDA kernels this library has launched from the calling host thread so far
+ * (thread-local tally; bench.py reports its difference over the timed region as gpu_launches). */
+int64_t vae_launch_count(void);
 /* FP32 FFMA throughput probe (the roofline denominator for the small-model
  * configs): runs `iters` dependent-chain FFMA batches on every SM; d_sink device
  * float[>= blocks*threads]; *flops_out = total flops issued. */

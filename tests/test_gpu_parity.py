@@ -421,6 +421,49 @@ def test_fused_packed_equals_single(ops, lib):
             assert torch.equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("case_idx,n_jobs,batch", [(7, 8, 100), (7, 4, 37), (0, 8, 100), (12, 2, 100), (9, 6, 64), (13, 8, 100)])
+def test_fused_cluster_shared_eps_is_bit_identical(ops, lib, case_idx, n_jobs, batch):
+    """Homogeneous packs run as thread-block clusters whose members with EQUAL carried model
+    keys share one eps draw per step (fused_small.cu).  Every model must come out bit-for-bit
+    as when it runs alone (cluster of one, private draw): same shape, different dataset seeds,
+    and a mix of equal / different model keys inside one cluster."""
+    n = 40
+    base = FUSED_CASES[case_idx]
+    alt_keys = {2: jr.PRNGKey(123), 5: jr.PRNGKey(123), 3: jr.PRNGKey(7)}      # job index -> different model chain
+    singles, packed, jobs = [], [], []
+    for i in range(n_jobs):
+        case = base[:6] + (base[6] + i,)                         # dataset seed varies
+        for dest in (singles, packed):
+            _, _, _, st, job = fused_setup(ops, lib, case, n, batch=batch)
+            if i in alt_keys:
+                st["mk"].copy_(ops.key_tensor(alt_keys[i]))
+            dest.append((st, job))
+    sc1 = ops.fused_scratch(1)
+    for st, job in singles:
+        ops.train_fused([job], n, sc1)
+        torch.cuda.synchronize()
+    ops.train_fused([j for _, j in packed], n, ops.fused_scratch(n_jobs))
+    torch.cuda.synchronize()
+    for (a, _), (b, _) in zip(singles, packed):
+        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+            assert torch.equal(a[k], b[k]), k
+    # chunked launches of the pack carry the state exactly as one launch does
+    again = []
+    for i in range(n_jobs):
+        _, _, _, st, job = fused_setup(ops, lib, base[:6] + (base[6] + i,), n, batch=batch)
+        if i in alt_keys:
+            st["mk"].copy_(ops.key_tensor(alt_keys[i]))
+        again.append((st, job))
+    sc = ops.fused_scratch(n_jobs)
+    for chunk in (1, 9, 30):
+        ops.train_fused([j for _, j in again], chunk, sc)
+        torch.cuda.synchronize()
+    for (a, _), (b, _) in zip(packed, again):
+        for k in ("P", "M", "V", "mk", "dk", "step"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a["loss"][10:40], b["loss"][:30])
+
+
 def test_fused_fixed_variance_and_odd_batch(ops, lib):
     for batch, tunable in ((100, False), (37, True), (33, False)):
         case = FUSED_CASES[8]
@@ -613,3 +656,91 @@ def test_fused_cluster_packed_and_chunked(ops, lib):
         for k in ("P", "M", "V", "mk", "dk", "step"):
             assert torch.equal(a[k], b[k]), k
         assert torch.equal(a["loss"][:4], b["loss"][2:6])
+
+
+# ------------------------------------------------------- long runs (north_star: 1e-3 after 10k steps)
+
+LONG_CASES = [
+    # (fused case, steps)
+    (("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2), 10000),     # BASELINE configs[0]
+    (("sigmoid", 3, 3, 6, 1e-4, -3.0, 69), 10000),             # BASELINE configs[1]
+    (("sigmoid", 7, 20, 24, 1e-4, -3.0, 48), 10000),
+]
+
+
+def _c_oracle_job(d, ds, name, dd, pd, flat, mkey, dkey, n):
+    from oracle import c_oracle as co
+    return co, co.Job(co.make_desc(d), co.make_data(name, dd, pd), flat, mkey, dkey, ds.A, n)
+
+
+def _long_run_checks(d, lossg, lossc, Pg, Pc, n):
+    """Loss curve, parameters and the learned variances after n steps: GPU float32 vs the C
+    oracle float32 (same op order is NOT assumed -- two independent float32 roundings of the
+    same chain -- so the bars are north_star's 'rel 1e-3 after 10k steps')."""
+    assert np.isfinite(lossg).all()
+    # ELBO curve: the last 500 steps agree to 1e-3 of the loss scale, step by step
+    tail = slice(n - 500, n)
+    scale = np.maximum(np.abs(lossc[tail]), 1.0)
+    assert np.max(np.abs(lossg[tail] - lossc[tail]) / scale) <= 1e-3
+    # the implicit-bias quantities: encoder log-variances epsilon_p (L,) and the decoder
+    # log-variance epsilon * eps0 (vae.py:137-138)
+    segs = {nm: (off, int(np.prod(shape))) for nm, shape, off in d.segments()}
+    off, cnt = segs["epsilon_p"]
+    np.testing.assert_allclose(Pg[off:off + cnt], Pc[off:off + cnt], rtol=1e-3, atol=1e-3)
+    if "epsilon" in segs:
+        off, cnt = segs["epsilon"]
+        np.testing.assert_allclose(Pg[off] * d.epsilon0, Pc[off] * d.epsilon0, rtol=1e-3, atol=1e-3)
+    # every parameter: rel 1e-3 of the parameter scale (plus 1e-3 absolute for coordinates near 0)
+    assert np.max(np.abs(Pg - Pc)) <= 1e-3 * max(1.0, np.max(np.abs(Pc)))
+
+
+@pytest.mark.parametrize("case,n", LONG_CASES, ids=lambda v: f"{v[0]}_dd{v[1]}_pd{v[2]}_L{v[3]}" if isinstance(v, tuple) else str(v))
+def test_fused_small_long_run(ops, lib, case, n):
+    d, ds, tr, st, job = fused_setup(ops, lib, case, n)
+    name, dd, pd = case[0], case[1], case[2]
+    flat = st["P"].cpu().numpy().copy()
+    co, cj = _c_oracle_job(d, ds, name, dd, pd, flat, tr.key, ds.key, n)
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    co.train_loop([cj], n, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), cj.model_key)      # 10k splits later: still bit-exact
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), cj.dataset_key)
+    _long_run_checks(d, st["loss"].cpu().numpy().astype(np.float64), cj.loss[:n].astype(np.float64),
+                     st["P"].cpu().numpy().astype(np.float64), cj.params.astype(np.float64), n)
+
+
+def test_fused_cluster_long_run(ops, lib):
+    """Sphere sweep shape (BASELINE configs[2]: dd=3 pd=3 L=6, 200x3 hidden), 1000 steps.
+    Hidden relu layers make the chain sensitive to float32 rounding: two float32 runs of the
+    SAME algorithm drift apart.  The bar is therefore self-calibrated: the GPU run must stay
+    within 4x the drift between the C oracle and the C oracle restarted from parameters
+    perturbed by one float32 ulp (plus north_star's 1e-3), for the ELBO curve, the learned
+    variances and all parameters."""
+    n = 1000
+    case = ("sphere", 3, 3, 6, [200, 200, 200], [200, 200, 200], 100, 69)
+    d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
+    flat = st["P"].cpu().numpy().copy()
+    co, cj = _c_oracle_job(d, ds, "sphere", 3, 3, flat, tr.key, ds.key, n)
+    _, cp = _c_oracle_job(d, ds, "sphere", 3, 3, np.nextafter(flat, np.float32(np.inf)), tr.key, ds.key, n)
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    co.train_loop([cj, cp], n, 2)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), cj.model_key)
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), cj.dataset_key)
+    lg, lc, lp = (a[:n].astype(np.float64) for a in (st["loss"].cpu().numpy(), cj.loss, cp.loss))
+    Pg, Pc, Pp = (a.astype(np.float64) for a in (st["P"].cpu().numpy(), cj.params, cp.params))
+    assert np.isfinite(lg).all()
+    # first 100 steps: still tight (rel 1e-4), before the drift is amplified
+    assert np.max(np.abs(lg[:100] - lc[:100]) / np.abs(lc[:100])) <= 1e-4
+    tail = slice(n - 300, n)
+    scale = np.maximum(np.abs(lc[tail]), 1.0)
+    drift_loss = np.max(np.abs(lp[tail] - lc[tail]) / scale)
+    assert np.max(np.abs(lg[tail] - lc[tail]) / scale) <= 4 * drift_loss + 1e-3, drift_loss
+    assert abs(lg[tail].mean() - lc[tail].mean()) <= 2e-3 * abs(lc[tail].mean())
+    segs = {nm: (off, int(np.prod(shape))) for nm, shape, off in d.segments()}
+    for nm in ("epsilon_p", "epsilon"):                       # the learned variances (vae.py:137-138)
+        off, cnt = segs[nm]
+        drift = np.max(np.abs(Pp[off:off + cnt] - Pc[off:off + cnt]))
+        assert np.max(np.abs(Pg[off:off + cnt] - Pc[off:off + cnt])) <= 4 * drift + 1e-3, (nm, drift)
+    drift_p = np.max(np.abs(Pp - Pc))
+    assert np.max(np.abs(Pg - Pc)) <= 4 * drift_p + 1e-3, drift_p

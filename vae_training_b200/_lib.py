@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvae_b200.so")
+LIB_PATH = os.environ.get("VAE_B200_LIB") or os.path.join(HERE, "libvae_b200.so")      # override: A/B builds
 VAE_MAX_HIDDEN = 8
 
 DATA_KINDS = {"sphere": 0, "linear_gaussian": 1, "sigmoid": 2}
@@ -77,6 +77,7 @@ _PROTOTYPES = {
                                      C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
     "vae_last_error": (C.c_char_p, []),
     "vae_abi_version": (C.c_int, []),
+    "vae_launch_count": (C.c_int64, []),
     "vae_ffma_probe": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _P]),
 }
 

@@ -14,14 +14,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libvae_b200.so")
+LIB = os.environ.get("VAE_B200_LIB") or os.path.join(HERE, "libvae_b200.so")      # override: A/B builds
+if os.environ.get("VAE_B200_LIB"):
+    OBJ = OBJ + "_" + os.path.basename(LIB).replace(".", "_")
 HEADER = os.path.join(HERE, "..", "include", "vae_b200.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2",
-] + ([f"-DVAE_SMALL_MAXB={os.environ['VAE_SMALL_MAXB']}"] if os.environ.get("VAE_SMALL_MAXB") else [])
+] + [f"-D{k}={os.environ[k]}" for k in ("VAE_SMALL_MAXB", "VAE_SMALL_GM_MODELS") if os.environ.get(k)]
 
 
 def find_nvcc() -> str:

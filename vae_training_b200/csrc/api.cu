@@ -15,6 +15,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int64_t g_launches = 0;
+void count_launch() { ++g_launches; }
+int64_t launch_count() { return g_launches; }
+
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
@@ -96,6 +100,7 @@ int32_t vae_data_normals_per_row(const VaeDataDesc* d) {
 
 const char* vae_last_error(void) { return vae::g_err; }
 int vae_abi_version(void) { return VAE_B200_ABI_VERSION; }
+int64_t vae_launch_count(void) { return vae::launch_count(); }
 
 }  // extern "C"
 

@@ -14,6 +14,7 @@ namespace vae {
 
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launch();      // thread-local tally behind vae_launch_count()
 
 #define VAE_CUDA_OK(call)                                   \
   do {                                                      \
@@ -24,6 +25,7 @@ int check_cuda(cudaError_t e, const char* what);
   do {                                                      \
     int _rc = ::vae::check_cuda(cudaGetLastError(), name);  \
     if (_rc != 0) return _rc;                               \
+    ::vae::count_launch();                                  \
   } while (0)
 #define VAE_REQUIRE(cond, ...)                              \
   do {                                                      \

@@ -597,6 +597,7 @@ int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cud
   attr[0].val.clusterDim.x = kMlpMaxCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)d_jobs, n_steps));
+  count_launch();
   return 0;
 }
 

@@ -23,11 +23,14 @@
 //   phase C (thread per tile)    dW tiles (TI x TJ) = sum_b h[i][b] d[j][b] with 128-bit
 //                                loads along the batch, split-K over KS adjacent lanes,
 //                                shuffle reduce, Adam, publish new weights
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vae {
 
 constexpr int kT = 128;
+constexpr int kGroupBatch = 100;      // batch size the GM > 1 kernels are compiled for (run.py:14 default)
 #ifndef VAE_SMALL_MAXB
 #define VAE_SMALL_MAXB 8
 #endif
@@ -87,7 +90,9 @@ struct SmallCfg {
   struct Lay {
     int P, M, V, sl, el, kt, scal, red, A, keys, z, gn, hx, hz, dm, dx, dp, q, total, BP;
   };
-  __host__ __device__ static Lay layout(int B) {
+  // nbuf = 2 when the launch uses clusters: eps (z) and the generator normals (gn) are then
+  // double-buffered by step parity (they are drawn one step ahead, see fused_small_run)
+  __host__ __device__ static Lay layout(int B, int nbuf) {
     Lay y; int o = 0;
     const int BP = batch_stride(B);
     y.BP = BP;
@@ -98,15 +103,15 @@ struct SmallCfg {
     y.red = o; o += 16;            // [3][4] warp partials
     y.A = o; o += up4(AN + 1);
     y.keys = o; o += 8;            // uint32 [2 slots][lat0 lat1 bat0 bat1]
-    y.z = o; o += up4(B * SZ);
-    y.gn = o; o += up4(B * SG);
+    y.z = o; o += nbuf * up4(B * SZ);
+    y.gn = o; o += nbuf * up4(B * SG);
     y.hx = o; o += (DR + 1) * BP;  // transposed from here on: [feature][BP]
     y.hz = o; o += (L + 1) * BP;
     y.dm = o; o += L * BP;
     y.dx = o; o += D * BP;
     y.dp = o; o += SIG ? D * BP : 0;
     y.q = o; o += L * BP;
-    y.total = o;
+    y.total = up4(o);
     return y;
   }
   // flat (include/vae_b200.h) parameter index -> padded on-chip offset, -1 if never touched
@@ -139,15 +144,115 @@ __device__ __forceinline__ float approx_sqrt(float x) {
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
+// ---- thread-block-cluster helpers (shared eps draw, see fused_small_run)
+__device__ __forceinline__ uint32_t cl_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// shared::cta address -> the same offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cl_st(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// One step's random draws: this CTA's slice [e_lo, e_hi) of the eps block pairs (all of them
+// when the CTA draws privately) and, when do_ds, all block pairs of the generator normals, as
+// ONE index space spread over the CTA's threads; each thread-iteration owns an adjacent pair
+// of threefry blocks (two independent chains in flight).  kq = [latent key | batch key].
+// remote: eps normals are stored into the z buffer of every cluster CTA in gmask (DSMEM).
+// mode 0: eps goes to this model's own z; mode 1: to the z of every cluster CTA in gmask
+// (DSMEM); mode 2: to the z of every model of THIS CTA in gmask (models are mstride floats apart,
+// this model is number mi).
 template <class C>
-__device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* sm) {
+__device__ __noinline__ void small_draw(float* zdst, float* gdst, const uint32_t* kq, int B, int e_lo, int e_hi,
+                                        uint32_t gmask, int mode, int t, int mi, int mstride) {
+  constexpr int LD = C::L + C::D, G = C::G;
+  const uint32_t lk0 = kq[0], lk1 = kq[1], bk0 = kq[2], bk1 = kq[3];
+  const int n_e = B * LD, half_e = (n_e + 1) >> 1, n_d = B * G, half_d = (n_d + 1) >> 1;
+  const int ne = e_hi - e_lo, nd = (half_d + 1) >> 1;
+  const uint32_t zaddr = (uint32_t)__cvta_generic_to_shared(zdst);
+  // Iterations are dealt out from the LAST thread down, so the partial final round lands on warp 3
+  // -- the warp with the least phase-C work (phase C -> next draw has no barrier in between).
+#pragma unroll 1
+  for (int it = kT - 1 - t; it < ne + nd; it += kT) {
+    const bool isd = it >= ne;
+    const int pi = isd ? it - ne : e_lo + it;
+    const uint32_t k0 = isd ? bk0 : lk0, k1 = isd ? bk1 : lk1;
+    const int half = isd ? half_d : half_e, n = isd ? n_d : n_e;
+    const int ja = 2 * pi, jb = 2 * pi + 1;
+    const bool vb = jb < half, v1 = ja + half < n, v3 = vb && jb + half < n;
+    uint32_t a0 = (uint32_t)ja, a1 = v1 ? (uint32_t)(ja + half) : 0u;
+    uint32_t b0 = vb ? (uint32_t)jb : 0u, b1 = v3 ? (uint32_t)(jb + half) : 0u;
+    threefry2x32_x2(k0, k1, a0, a1, k0, k1, b0, b1);
+    const float n0 = normal_from_bits_fast(a0), n1 = normal_from_bits_fast(a1);
+    const float n2 = normal_from_bits_fast(b0), n3 = normal_from_bits_fast(b1);
+    auto off_of = [&](int j) -> int {
+      const int oe = C::SZ == LD ? j : (j / LD) * C::SZ + j % LD;
+      const int od = C::SG == G ? j : (j / G) * C::SG + j % G;
+      return isd ? od : oe;
+    };
+    const int o0 = off_of(ja), o1 = off_of(v1 ? ja + half : ja), o2 = off_of(vb ? jb : ja), o3 = off_of(v3 ? jb + half : ja);
+    if (isd || mode == 0) {
+      float* dst = isd ? gdst : zdst;
+      dst[o0] = n0;
+      if (v1) dst[o1] = n1;
+      if (vb) dst[o2] = n2;
+      if (v3) dst[o3] = n3;
+    } else if (mode == 2) {           // the same four stores into the z of every group member of this CTA
+      for (uint32_t m = gmask; m; m &= m - 1u) {
+        float* dst = zdst + ((__ffs((int)m) - 1) - mi) * mstride;
+        dst[o0] = n0;
+        if (v1) dst[o1] = n1;
+        if (vb) dst[o2] = n2;
+        if (v3) dst[o3] = n3;
+      }
+    } else {                          // ... of every group member of the cluster
+      for (uint32_t m = gmask; m; m &= m - 1u) {
+        const uint32_t rb = cl_mapa(zaddr, (uint32_t)__ffs((int)m) - 1u);
+        cl_st(rb + 4u * (uint32_t)o0, n0);
+        if (v1) cl_st(rb + 4u * (uint32_t)o1, n1);
+        if (vb) cl_st(rb + 4u * (uint32_t)o2, n2);
+        if (v3) cl_st(rb + 4u * (uint32_t)o3, n3);
+      }
+    }
+  }
+}
+
+// Shared eps draw.  The reference's model key is always PRNGKey(0) (model.py:29), so the runs
+// of a sweep that have the same (B, L + D) draw the SAME eps stream (vae.py:125-126,
+// model.py:227) and differ only in their dataset chain.  When the launch groups CTAs into
+// thread-block clusters, every CTA compares its carried model key with its cluster peers' ON
+// THE DEVICE; the CTAs that hold equal keys form a group, each member draws 1/|group| of the
+// step's threefry blocks and stores the normals into every member's shared memory through
+// DSMEM.  Values are bit-identical to a private draw; a CTA whose key matches nobody is a
+// group of one and draws everything itself.
+// Cluster launches run the draws ONE STEP AHEAD into double-buffered z / gn:
+//   B_s (reads z[s&1]) ; draw_{s+1} -> z[(s+1)&1] of the group ; cluster arrive ; CTA barrier ;
+//   C_s ; cluster wait ; CTA barrier
+// so the only cluster-wide dependency ("eps of step s+1 is complete everywhere") has the
+// whole of phase C as slack between arrive and wait.  The wait of iteration s-1 also proves
+// that every peer finished B_{s-1}, the last reader of the buffer draw_{s+1} overwrites.
+// GM > 1: one CTA of GM * 128 threads runs GM models side by side (threads [128 m, 128 m + 128)
+// own model m and its slice of shared memory); the models of a CTA that hold equal keys form
+// the eps-sharing group (plain shared-memory stores, CTA barriers only) -- used without clusters.
+// BT > 0 fixes the batch size at compile time (the grouped kernels are built for the reference's
+// batch of 100, run.py:14): the whole shared-memory layout becomes immediate offsets.
+template <class C, int GM, int BT>
+__device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float* sm_cta) {
   constexpr int D = C::D, L = C::L, DR = C::DR, DD = C::DD, G = C::G, LP = C::LP, DP = C::DP;
   constexpr int TI = C::TI, TJ = C::TJ, KS = C::KS;
   constexpr int LD = L + D;
-  const int t = threadIdx.x;
-  const int B = job.batch;
+  const int mi = GM > 1 ? (int)threadIdx.x / kT : 0;             // model within the CTA
+  const int t = GM > 1 ? (int)threadIdx.x % kT : (int)threadIdx.x;
+  const FusedJobDev job = jobs[(int)blockIdx.x * GM + mi];
+  const int B = BT > 0 ? BT : job.batch;
   const bool tunable = job.tunable != 0;
-  const typename C::Lay y = C::layout(B);
+  const uint32_t csize = cl_nctarank(), crank = cl_ctarank();
+  const bool pipe = csize > 1;           // cluster launch: draws run one step ahead (double-buffered)
+  const typename C::Lay y = C::layout(B, pipe ? 2 : 1);
+  float* sm = sm_cta + mi * y.total;       // y.total is a multiple of 4 floats
   const int BP = y.BP, NG = BP >> 2;
   float* P = sm + y.P; float* M = sm + y.M; float* V = sm + y.V;
   uint32_t* keys = reinterpret_cast<uint32_t*>(sm + y.keys);
@@ -202,60 +307,60 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     keys[slot * 4 + t] = used;          // [lat0 lat1 bat0 bat1]
   };
   if (t < 4 && n_steps > 0) advance_keys(0);
+  // ---- eps-sharing group inside the cluster (a cluster of one: no cluster instructions at all)
+  // members: the cluster's CTAs (GM == 1) or this CTA's models (GM > 1, never both)
+  const uint32_t self = GM > 1 ? (uint32_t)mi : crank;
+  const uint32_t nmemb = GM > 1 ? (uint32_t)GM : csize;
+  uint32_t gmask = 1u << self;
+  if (nmemb > 1) {
+    const uint32_t mk0 = job.model_key[0], mk1 = job.model_key[1];
+    const FusedJobDev* peers = GM > 1 ? jobs + (int)blockIdx.x * GM : jobs + ((int)blockIdx.x - (int)crank);
+    gmask = 0u;
+    for (uint32_t r = 0; r < nmemb; ++r) {
+      const FusedJobDev& o = peers[r];
+      if (o.model_key[0] == mk0 && o.model_key[1] == mk1 && o.batch == job.batch && o.shape_id == job.shape_id)
+        gmask |= 1u << r;
+    }
+  }
+  const int gsize = __popc(gmask), gidx = __popc(gmask & ((1u << self) - 1u));
+  const int draw_mode = gsize == 1 ? 0 : GM > 1 ? 2 : 1;
   __syncthreads();
 
   const float invB = 1.0f / (float)B;
-  const int half_e = (B * LD + 1) >> 1, n_e = B * LD;
-  const int half_d = (B * G + 1) >> 1, n_d = B * G;
+  const int npair_e = (((B * LD + 1) >> 1) + 1) >> 1;     // eps block pairs per step
+  int e_lo = 0, e_hi = npair_e;                            // this CTA's slice of them
+  if (gsize > 1) {
+    const int chunk = (npair_e + gsize - 1) / gsize;
+    e_lo = min(npair_e, gidx * chunk);
+    e_hi = min(npair_e, e_lo + chunk);
+  }
+  const int zstride = up4(B * C::SZ), gstride = up4(B * C::SG);
+  // draws of step q: keys[q&1] -> z / gn buffer (q&1 when pipelined); lanes 0-3 then advance the
+  // key chains for step q+1 into the other slot
+  auto draw_step = [&](int64_t q) {
+    const int qs = (int)(q & 1), buf = pipe ? qs : 0;
+    small_draw<C>(sm + y.z + buf * zstride, sm + y.gn + buf * gstride, keys + qs * 4, B, e_lo, e_hi, gmask, draw_mode, t, mi, y.total);
+    if (t < 4 && q + 1 < n_steps) advance_keys(qs ^ 1);
+  };
+  if (pipe) {
+    cl_arrive(); cl_wait();       // every peer's shared memory is initialised and its keys are read
+    if (n_steps > 0) draw_step(0);
+    cl_arrive(); cl_wait();       // eps of step 0 complete everywhere
+  }
 
   for (int64_t s = 0; s < n_steps; ++s) {
     const int slot = (int)(s & 1);
-    // ================= phase A: random draws (two independent threefry blocks in flight)
-    {
-      const uint32_t lk0 = keys[slot * 4 + 0], lk1 = keys[slot * 4 + 1];
-      const uint32_t bk0 = keys[slot * 4 + 2], bk1 = keys[slot * 4 + 3];
-      if (t < 4 && s + 1 < n_steps) advance_keys(slot ^ 1);
-      // Two passes over ONE loop body (eps draw, generator draw): keys / extents / destination
-      // are pass constants, and each thread-iteration owns an adjacent pair of threefry blocks
-      // (two independent chains in flight).
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t k0 = pass ? bk0 : lk0, k1 = pass ? bk1 : lk1;
-        const int half = pass ? half_d : half_e, n = pass ? n_d : n_e;
-        float* dst = sm + (pass ? y.gn : y.z);
-        auto off_of = [&](int j) -> int {
-          const int oe = C::SZ == LD ? j : (j / LD) * C::SZ + j % LD;
-          const int od = C::SG == G ? j : (j / G) * C::SG + j % G;
-          return pass ? od : oe;
-        };
-        const int npair = (half + 1) >> 1;
-#pragma unroll 1
-        for (int pi = t; pi < npair; pi += kT) {
-          const int ja = 2 * pi, jb = 2 * pi + 1;
-          const bool vb = jb < half;
-          uint32_t a0 = (uint32_t)ja, a1 = ja + half < n ? (uint32_t)(ja + half) : 0u;
-          uint32_t b0 = vb ? (uint32_t)jb : 0u, b1 = (vb && jb + half < n) ? (uint32_t)(jb + half) : 0u;
-          threefry2x32_x2(k0, k1, a0, a1, k0, k1, b0, b1);
-          const float n0 = normal_from_bits_fast(a0), n1 = normal_from_bits_fast(a1);
-          const float n2 = normal_from_bits_fast(b0), n3 = normal_from_bits_fast(b1);
-          dst[off_of(ja)] = n0;
-          if (ja + half < n) dst[off_of(ja + half)] = n1;
-          if (vb) {
-            dst[off_of(jb)] = n2;
-            if (jb + half < n) dst[off_of(jb + half)] = n3;
-          }
-        }
-      }
-    }
-    __syncthreads();
+    const int zb = pipe ? slot : 0;
+    // ================= phase A: random draws (private mode: in step; cluster mode: one step ahead)
+    if (!pipe) { draw_step(s); __syncthreads(); }
     // ================= phase B: one thread per batch row
     float kl_acc = 0.f, r2_acc = 0.f, rz_acc = 0.f;
     {
       const float sd = sm[y.scal + 8 * slot + 1], inv_var = sm[y.scal + 8 * slot + 2];
       const float gscale = inv_var * invB;
       for (int b = t; b < B; b += kT) {
-        const float* zr = sm + y.z + b * C::SZ;
-        const float* gr = sm + y.gn + b * C::SG;
+        const float* zr = sm + y.z + zb * zstride + b * C::SZ;
+        const float* gr = sm + y.gn + zb * gstride + b * C::SG;
         // ---- generator transform (bit-exact with oracle/datasets.py)
         float x[DR];
         if constexpr (C::KIND == VAE_DATA_SPHERE) {
@@ -378,6 +483,10 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
         sm[y.red + 0 + (t >> 5)] = kl_acc; sm[y.red + 4 + (t >> 5)] = r2_acc; sm[y.red + 8 + (t >> 5)] = rz_acc;
       }
     }
+    if (pipe) {                     // next step's draws; then "my share of eps_{s+1} is stored everywhere"
+      if (s + 1 < n_steps) draw_step(s + 1);
+      cl_arrive();
+    }
     __syncthreads();
     // ================= phase C: gradient tiles + Adam
     {
@@ -492,6 +601,7 @@ __device__ void fused_small_run(const FusedJobDev& job, int64_t n_steps, float* 
     }
     // no barrier here: phase A of the next step touches only z / gn / keys, which phase C
     // does not read; the A->B barrier orders the parameter writes before the next reads.
+    if (pipe) { cl_wait(); __syncthreads(); }     // eps_{s+1} complete everywhere; phase C done in this CTA
   }
   __syncthreads();
   // ---- store state
@@ -531,7 +641,7 @@ fused_small_kernel(const FusedJobDev* __restrict__ jobs, int64_t n_steps) {
   const FusedJobDev job = jobs[blockIdx.x];
   switch (job.shape_id) {
 #define X(id, D, L, DR, SIG, KIND, G, TI, TJ) \
-    case id: fused_small_run<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>(job, n_steps, sm); break;
+    case id: fused_small_run<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1, 0>(jobs, n_steps, sm); break;
     VAE_SMALL_SHAPES(X)
 #undef X
     default: break;
@@ -539,16 +649,15 @@ fused_small_kernel(const FusedJobDev* __restrict__ jobs, int64_t n_steps) {
 }
 
 // homogeneous packs: a kernel per shape, so registers / occupancy are the shape's own
-template <class C>
-__global__ void __launch_bounds__(kT, C::MINB)
+template <class C, int GM>
+__global__ void __launch_bounds__(kT * GM, (C::MINB / GM) > 0 ? (C::MINB / GM) : 1)
 fused_small_kernel_one(const FusedJobDev* __restrict__ jobs, int64_t n_steps) {
   extern __shared__ __align__(16) float sm[];
-  const FusedJobDev job = jobs[blockIdx.x];
-  fused_small_run<C>(job, n_steps, sm);
+  fused_small_run<C, GM, (GM > 1 ? kGroupBatch : 0)>(jobs, n_steps, sm);
 }
 
 // Returns the shape id (>= 0) or -1; *smem_floats receives the CTA's shared memory need.
-static int small_shape_of(const VaeTrainJob* j, int* smem_floats) {
+static int small_shape_of(const VaeTrainJob* j, int* smem_floats, int nbuf = 1) {
   const VaeDesc& d = j->desc;
   const VaeDataDesc& g = j->data;
   if (d.n_enc_hidden != 0 || d.n_dec_hidden != 0) return -1;
@@ -560,7 +669,7 @@ static int small_shape_of(const VaeTrainJob* j, int* smem_floats) {
   const int gg = g.kind == VAE_DATA_LINEAR_GAUSSIAN ? g.intrinsic_dim : g.dim;
 #define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                \
   if (d.data_dim == D && d.latent_dim == L && dr == DR && g.kind == KIND && gg == G) {       \
-    *smem_floats = SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>::layout(d.batch).total;          \
+    *smem_floats = SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>::layout(d.batch, nbuf).total;          \
     return id;                                                                               \
   }
   VAE_SMALL_SHAPES(X)
@@ -570,45 +679,113 @@ static int small_shape_of(const VaeTrainJob* j, int* smem_floats) {
 
 constexpr int kMaxSmem = 227 * 1024;
 
-static int launch_small(int shape_id, bool homogeneous, int n_jobs, size_t smem, const FusedJobDev* d_jobs,
+// VAE_SMALL_CLUSTER=n caps the cluster size, VAE_SMALL_GM=n the models per CTA (1 = off; A/B runs)
+static int env_cap(const char* name, int dflt, int hi) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  const int v = atoi(e);
+  return v < 1 ? 1 : v > hi ? hi : v;
+}
+#ifndef VAE_SMALL_GM_MODELS
+#define VAE_SMALL_GM_MODELS 4
+#endif
+constexpr int kGM = VAE_SMALL_GM_MODELS;   // models per CTA of the grouped kernels
+
+// How a homogeneous pack of n_jobs models is launched: GM models per CTA (eps shared inside the
+// CTA) when the pack divides and GM footprints fit one SM's shared memory; otherwise one model
+// per CTA in clusters of two (eps shared through DSMEM; pairs tile every GPC, larger clusters
+// strand SMs); otherwise plain CTAs.
+struct SmallPlan { int gm, cluster, nbuf; size_t smem; };
+static SmallPlan plan_small(const VaeTrainJob* job0, int n_jobs, bool homogeneous) {
+  SmallPlan p = {1, 1, 1, 0};
+  int fl1 = 0, fl2 = 0;
+  small_shape_of(job0, &fl1, 1);
+  small_shape_of(job0, &fl2, 2);
+  p.smem = (size_t)fl1 * 4;
+  if (!homogeneous) return p;
+  if (env_cap("VAE_SMALL_GM", kGM, kGM) == kGM && n_jobs % kGM == 0 && job0->desc.batch == kGroupBatch && (size_t)fl1 * 4 * kGM <= (size_t)kMaxSmem) {
+    p.gm = kGM; p.smem = (size_t)fl1 * 4 * kGM;
+    return p;
+  }
+  if (env_cap("VAE_SMALL_CLUSTER", 2, 8) >= 2 && n_jobs % 2 == 0 && (size_t)fl2 * 4 <= (size_t)kMaxSmem) {
+    int c = 2;
+    const int cap = env_cap("VAE_SMALL_CLUSTER", 2, 8);
+    while (c * 2 <= cap && n_jobs % (c * 2) == 0) c *= 2;
+    p.cluster = c; p.nbuf = 2; p.smem = (size_t)fl2 * 4;
+  }
+  return p;
+}
+
+template <class K>
+static int launch_one(K k, int n_ctas, int threads, int cluster, size_t smem, const FusedJobDev* d_jobs, int64_t n_steps,
+                      cudaStream_t s) {
+  VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_ctas, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, k, d_jobs, n_steps));
+  return 0;
+}
+
+static int launch_small(int shape_id, bool homogeneous, const SmallPlan& p, int n_jobs, const FusedJobDev* d_jobs,
                         int64_t n_steps, cudaStream_t s) {
   if (homogeneous) {
+    int rc = 0;
     switch (shape_id) {
 #define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                              \
-      case id: {                                                                                           \
-        auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>;                         \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
-        k<<<n_jobs, kT, smem, s>>>(d_jobs, n_steps);                                                       \
-        break;                                                                                             \
-      }
+      case id:                                                                                             \
+        if (p.gm == kGM)                                                                                   \
+          rc = launch_one(fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, kGM>,           \
+                          n_jobs / kGM, kT * kGM, 1, p.smem, d_jobs, n_steps, s);                          \
+        else                                                                                               \
+          rc = launch_one(fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1>, n_jobs, kT, \
+                          p.cluster, p.smem, d_jobs, n_steps, s);                                          \
+        break;
       VAE_SMALL_SHAPES(X)
 #undef X
       default: set_error("bad shape id %d", shape_id); return VAE_ERR_INVALID;
     }
+    if (rc) return rc;
   } else {
-    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    fused_small_kernel<<<n_jobs, kT, smem, s>>>(d_jobs, n_steps);
+    fused_small_kernel<<<n_jobs, kT, p.smem, s>>>(d_jobs, n_steps);
   }
   VAE_LAUNCH_OK("fused_small_kernel");
   return 0;
 }
 
-static int occupancy_small(int shape_id, size_t smem, int* out) {
+// models resident per SM when a full homogeneous pack of this shape is launched (plan_small)
+static int occupancy_small(int shape_id, const SmallPlan& p, int* out) {
+  int blocks = 0;
   switch (shape_id) {
 #define X(id, D, L, DR, SIG, KIND, G, TI, TJ)                                                              \
-    case id: {                                                                                           \
-      auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>>;                         \
-      VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-      VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
-      VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, kT, smem));                      \
-      break;                                                                                             \
+    case id: {                                                                                             \
+      if (p.gm == kGM) {                                                                                   \
+        auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, kGM>;                    \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));    \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kT * kGM, p.smem));          \
+      } else {                                                                                             \
+        auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1>;                      \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));    \
+        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kT, p.smem));                \
+      }                                                                                                    \
+      break;                                                                                               \
     }
     VAE_SMALL_SHAPES(X)
 #undef X
     default: set_error("bad shape id %d", shape_id); return VAE_ERR_INVALID;
   }
+  *out = blocks * p.gm;
   return 0;
 }
 
@@ -616,11 +793,13 @@ static int occupancy_small(int shape_id, size_t smem, int* out) {
 
 namespace vae {
 
+// models resident per SM as a full homogeneous pack of this shape is launched
 int small_ctas_per_sm(const VaeTrainJob* job) {
   int fl = 0, out = 0;
   const int id = small_shape_of(job, &fl);
   if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) return 0;
-  const int rc = occupancy_small(id, (size_t)fl * sizeof(float), &out);
+  const SmallPlan p = plan_small(job, 8 * kGM, true);
+  const int rc = occupancy_small(id, p, &out);
   return rc ? rc : out;
 }
 
@@ -672,8 +851,9 @@ int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, 
   const int shape0 = host[0].shape_id;
   free(host);
   VAE_CUDA_OK(e);
-  return launch_small(shape0, homogeneous, n_jobs, (size_t)max_fl * sizeof(float),
-                           (const FusedJobDev*)d_scratch, n_steps, s);
+  SmallPlan p = plan_small(&jobs[0], n_jobs, homogeneous);
+  if (!homogeneous) p.smem = (size_t)max_fl * sizeof(float);
+  return launch_small(shape0, homogeneous, p, n_jobs, (const FusedJobDev*)d_scratch, n_steps, s);
 }
 
 }  // namespace vae

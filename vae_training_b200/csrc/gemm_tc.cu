@@ -431,6 +431,7 @@ int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const
   cfg.attrs = attr; cfg.numAttrs = 1;
   VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, vae::gemm_nt_3xtf32_kernel<2>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
                                  flags));
+  vae::count_launch();
   return 0;
 }
 
