@@ -550,6 +550,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
         for (int ii = 0; ii < TI; ++ii)
 #pragma unroll
           for (int jj = 0; jj < TJ; ++jj) acc[ii][jj] = 0.f;
+#pragma unroll 2
         for (int g4 = ks; g4 < NG; g4 += KS) {
           float4 hv[TI], dv[TJ];
 #pragma unroll
@@ -626,7 +627,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   X(4, 12, 20, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
   X(5, 20, 10, 9, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)         \
   X(6, 20, 10, 12, false, VAE_DATA_LINEAR_GAUSSIAN, 3, 2, 4)        \
-  X(7, 7, 6, 4, true, VAE_DATA_SIGMOID, 3, 2, 2)                    \
+  X(7, 7, 6, 4, true, VAE_DATA_SIGMOID, 3, 2, 4)                    \
   X(8, 17, 8, 4, true, VAE_DATA_SIGMOID, 3, 2, 4)                   \
   X(9, 22, 16, 6, true, VAE_DATA_SIGMOID, 5, 4, 4)                  \
   X(10, 11, 10, 6, true, VAE_DATA_SIGMOID, 5, 2, 4)                 \
