@@ -32,12 +32,13 @@ def main():
     runs = sweep.builtin_runs(args.which, args.num_batches)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    models = sweep.run_sweep(runs, rank, world, save=False, verbose=False)
+    timings = {}
+    models = sweep.run_sweep(runs, rank, world, save=False, verbose=False, timings=timings)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     steps = sum(m.num_batches for m in models)
     summary = {"rank": rank, "world": world, "runs": len(models), "train_steps": steps, "seconds": dt,
-               "steps_per_sec": steps / dt, "results": []}
+               "steps_per_sec": steps / dt, **timings, "results": []}
     for m in models:
         losses = m.vae_losses
         summary["results"].append({
@@ -55,7 +56,8 @@ def main():
             wall = max(g["seconds"] for g in gathered)
             print(json.dumps({"world": world, "runs": sum(g["runs"] for g in gathered), "train_steps": tot,
                               "seconds_max_over_ranks": wall, "steps_per_sec": tot / wall,
-                              "per_rank_seconds": [round(g["seconds"], 2) for g in gathered]}), flush=True)
+                              "per_rank_seconds": [round(g["seconds"], 2) for g in gathered],
+                              "per_rank_train_seconds": [round(g.get("train_seconds", 0.0), 2) for g in gathered]}), flush=True)
             summary = {"ranks": gathered}
         dist.destroy_process_group()
     else:

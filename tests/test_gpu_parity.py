@@ -614,6 +614,26 @@ def test_fused_cluster_vs_oracle_loop(ops, lib, case):
     assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
 
 
+def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
+    """Small packs run each model on a 16-CTA (non-portable) cluster, large packs on 8 CTAs
+    (fused_mlp.cu:mlp_pick_cluster).  Column slices change, the arithmetic per output element
+    does not: both cluster sizes must agree bit for bit."""
+    n = 10
+    out = {}
+    for cs in ("8", "16"):
+        monkeypatch.setenv("VAE_MLP_CLUSTER", cs)
+        res = []
+        for case in (MLP_CASES[0], MLP_CASES[2], MLP_CASES[5], MLP_CASES[6]):
+            _, _, _, st, job = mlp_setup(ops, lib, case, n)
+            ops.train_fused([job], n, ops.fused_scratch(1))
+            torch.cuda.synchronize()
+            res.append(st)
+        out[cs] = res
+    for a, b in zip(out["8"], out["16"]):
+        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+            assert torch.equal(a[k], b[k]), k
+
+
 def test_fused_cluster_first_step_gradient_exact_path(ops, lib):
     """One step with adam_eps = 1 (well-conditioned): every parameter within 1e-3 * lr."""
     import dataclasses

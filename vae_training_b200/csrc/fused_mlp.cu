@@ -17,13 +17,16 @@
 // Exact work skipping: the generated batch has exactly-zero padding columns, so encoder layer
 // 0 uses only its first DR input rows and the other rows' gradients (exactly 0) are never
 // formed (Adam leaves those weights bit-for-bit unchanged).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vae {
 
 constexpr int kMT = 512;                       // threads per CTA
 constexpr int kML = VAE_MAX_HIDDEN + 1;        // max Dense layers per net
-constexpr int kMlpMaxCluster = 8;
+constexpr int kMlpMaxCluster = 8;          // portable cluster size: the throughput configuration
+constexpr int kMlpBigCluster = 16;         // non-portable: one model over 16 SMs (latency configuration)
 
 struct MlpJobDev {
   float* params; float* adam_m; float* adam_v; int32_t* step;
@@ -570,31 +573,48 @@ int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o) {
 
 size_t mlp_job_bytes() { return sizeof(MlpJobDev); }
 
-// clusters (= models) that can be resident at once on the current device
-int mlp_resident_jobs(size_t smem, int* out) {
+static int mlp_active_clusters(int cs, size_t smem, int* out) {
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kMlpMaxCluster * 64, 1, 1);
+  cfg.gridDim = dim3(cs * 64, 1, 1);
   cfg.blockDim = dim3(kMT, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kMlpMaxCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   VAE_CUDA_OK(cudaOccupancyMaxActiveClusters(out, fused_mlp_kernel, &cfg));
   return 0;
 }
 
+// clusters (= models) that can be resident at once on the current device (throughput packing)
+int mlp_resident_jobs(size_t smem, int* out) { return mlp_active_clusters(kMlpMaxCluster, smem, out); }
+
+// Cluster size of a launch.  A model's step is a serial chain of 17 cluster-wide phases, so a
+// pack that leaves SMs idle (e.g. the 2 sphere runs per GPU of the 8-GPU sweep) runs each model
+// on 16 CTAs instead of 8: half the GEMM / Adam / staging work per CTA and phase.  Packs that
+// need more than the co-resident 16-CTA clusters keep 8.  VAE_MLP_CLUSTER=8|16 overrides.
+static int mlp_pick_cluster(int n_jobs, size_t smem) {
+  const char* e = getenv("VAE_MLP_CLUSTER");
+  if (e && e[0]) return atoi(e) >= 16 ? kMlpBigCluster : kMlpMaxCluster;
+  int fit = 0;
+  if (mlp_active_clusters(kMlpBigCluster, smem, &fit) != 0) { cudaGetLastError(); return kMlpMaxCluster; }
+  return n_jobs <= fit ? kMlpBigCluster : kMlpMaxCluster;
+}
+
 int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s) {
+  const int cs = mlp_pick_cluster(n_jobs, smem);
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_jobs * kMlpMaxCluster), 1, 1);
+  cfg.gridDim = dim3((unsigned)(n_jobs * cs), 1, 1);
   cfg.blockDim = dim3(kMT, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kMlpMaxCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)d_jobs, n_steps));
   count_launch();

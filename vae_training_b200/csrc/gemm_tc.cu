@@ -124,8 +124,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // fetches half of Bh / Bl (64 rows) and TMA-multicasts it into both CTAs' shared memory, which
 // cuts the L2 -> SM operand traffic per CTA from 64 KB to 48 KB per k-block (the kernel is
 // L2-bandwidth bound: ncu shows 13 TB/s of xbar reads at 62 % tensor-pipe activity for MC = 1).
-// A stage may be refilled only when BOTH CTAs' MMAs have consumed it: tcgen05.commit arrives on
-// the empty barrier of both CTAs (count 2).
+// MC = 4: 2 x 2 clusters; the two CTAs with the same M tile additionally share their A tiles the
+// same way (32 KB per k-block per CTA).  Cluster rank = cx + CX * cy (cx along N, cy along M).
+// A stage may be refilled only when EVERY CTA that reads what this CTA multicasts has consumed it:
+// tcgen05.commit arrives on the empty barrier of this CTA and of its row / column partners.
 template <int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -144,7 +146,13 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int nchunk = (nkb + TC_CHUNK - 1) / TC_CHUNK;
-  const uint32_t crank = MC > 1 ? tc_cluster_ctarank() : 0u;       // position along M inside the cluster
+  constexpr int CX = MC == 4 ? 2 : 1, CY = MC >= 2 ? 2 : 1;         // cluster extent along N / along M
+  const uint32_t crank = MC > 1 ? tc_cluster_ctarank() : 0u;
+  const uint32_t cx = crank % CX, cy = crank / CX;
+  // CTAs with the same M tile (A partners) and with the same N tile (B partners), as rank masks
+  const uint16_t a_mask = (uint16_t)(((1u << CX) - 1u) << (cy * CX));
+  const uint16_t b_mask = (uint16_t)((1u << cx) | (CY > 1 ? 1u << (cx + CX) : 0u));
+  const uint16_t peers_mask = (uint16_t)(a_mask | b_mask);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAh)));
@@ -153,7 +161,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)));
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CX + CY - 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&mfull_bar[b], 1); mbar_init(&mempty_bar[b], 4); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,16 +186,23 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         mbar_wait(&empty_bar[s], ph ^ 1u);                 // slot free (first pass: immediately)
         uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
-        tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
-        tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
-        if (MC == 1) {
+        if (CX == 1) {
+          tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
+          tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
+        } else {      // this CTA's half of the A rows, multicast to the CTAs with the same M tile
+          const int half_rows = TC_BM / CX;
+          const size_t off = (size_t)cx * half_rows * TC_BK * 4;
+          tma_load_2d_mc(st + 0 * TC_TILE_BYTES + off, &tmAh, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
+          tma_load_2d_mc(st + 1 * TC_TILE_BYTES + off, &tmAl, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
+        }
+        if (CY == 1) {
           tma_load_2d(st + 2 * TC_TILE_BYTES, &tmBh, &full_bar[s], kb * TC_BK, n0);
           tma_load_2d(st + 3 * TC_TILE_BYTES, &tmBl, &full_bar[s], kb * TC_BK, n0);
-        } else {      // this CTA's half of the B rows, multicast to both CTAs of the cluster
-          const int half_rows = TC_BN / MC;
-          const size_t off = (size_t)crank * half_rows * TC_BK * 4;
-          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)crank * half_rows, (uint16_t)((1u << MC) - 1));
-          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)crank * half_rows, (uint16_t)((1u << MC) - 1));
+        } else {      // this CTA's half of the B rows, multicast to the CTAs with the same N tile
+          const int half_rows = TC_BN / CY;
+          const size_t off = (size_t)cy * half_rows * TC_BK * 4;
+          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
+          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
         }
       }
     }
@@ -218,7 +233,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           umma_tf32(tmem_small, dAl + adv, dBh + adv, idesc, 1u);
         }
         if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
-        else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << MC) - 1));
+        else umma_commit_mc(&empty_bar[s], peers_mask);
         if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) umma_commit(&mfull_bar[buf]);
       }
       umma_commit(&acc_bar);                               // every MMA of the tile complete
@@ -362,10 +377,37 @@ static int make_operand_map(CUtensorMap* tm, const float* ptr, int rows, int K, 
   return 0;
 }
 
-// VAE_TC_SINGLE_CTA=1 in the environment selects the non-multicast kernel (A/B comparison)
-static bool tc_force_single_cta() {
-  const char* e = getenv("VAE_TC_SINGLE_CTA");
-  return e && e[0] == '1';
+// VAE_TC_CLUSTER=1|2|4 in the environment caps the cluster size (A/B comparison).  Default 2:
+// measured on B200 (scratch/bench_gemm_ab.py, 65536 x 4096 x 4096 and 8192 x 4096 x 4096) the
+// 2 x 2 clusters are 8-17 % SLOWER than pairs -- clusters of four strand SMs (GPCs of 16/18/20
+// SMs) and the run is power-capped, so the lower L2 traffic buys nothing.
+static int tc_cluster_cap() {
+  const char* e = getenv("VAE_TC_CLUSTER");
+  if (!e || !e[0]) return 2;
+  const int v = atoi(e);
+  return v >= 4 ? 4 : v >= 2 ? 2 : 1;
+}
+
+template <int MC>
+static int launch_gemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
+                       float* d_C, int M, int N, int K, int64_t ldc, const float* d_bias, const float* d_mask, int64_t ldm,
+                       int flags, int tiles_n, int tiles_m, cudaStream_t stream) {
+  constexpr int CX = MC == 4 ? 2 : 1, CY = MC >= 2 ? 2 : 1;
+  VAE_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  // an odd last M tile is all out-of-bounds: zero-filled loads, masked stores
+  cfg.gridDim = dim3(tiles_n, (tiles_m + CY - 1) / CY * CY, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CX; attr[0].val.clusterDim.y = CY; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = MC > 1 ? 1 : 0;
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_nt_3xtf32_kernel<MC>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
+                                 flags));
+  count_launch();
+  return 0;
 }
 
 }  // namespace vae
@@ -405,34 +447,18 @@ int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const
   VAE_REQUIRE(!(flags & vae::TC_MASK) || (d_mask && ldm >= N), "vae_gemm_nt_3xtf32: mask is NULL / ldm too small");
   CUtensorMap tAh, tAl, tBh, tBl;
   int rc;
-  if ((rc = vae::make_operand_map(&tAh, d_Ah, M, K, lda))) return rc;
-  if ((rc = vae::make_operand_map(&tAl, d_Al, M, K, lda))) return rc;
   const int tiles_m = (M + vae::TC_BM - 1) / vae::TC_BM, tiles_n = (N + vae::TC_BN - 1) / vae::TC_BN;
-  const int mc = (tiles_m >= 2 && !vae::tc_force_single_cta()) ? 2 : 1;
-  if ((rc = vae::make_operand_map(&tBh, d_Bh, N, K, ldb, vae::TC_BN / mc))) return rc;
-  if ((rc = vae::make_operand_map(&tBl, d_Bl, N, K, ldb, vae::TC_BN / mc))) return rc;
-  if (mc == 1) {
-    VAE_CUDA_OK(cudaFuncSetAttribute(vae::gemm_nt_3xtf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, vae::TC_SMEM_BYTES));
-    dim3 grid(tiles_n, tiles_m);
-    vae::gemm_nt_3xtf32_kernel<1><<<grid, vae::TC_THREADS, vae::TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-        tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags);
-    VAE_LAUNCH_OK("gemm_nt_3xtf32_kernel<1>");
-    return 0;
-  }
-  VAE_CUDA_OK(cudaFuncSetAttribute(vae::gemm_nt_3xtf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, vae::TC_SMEM_BYTES));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles_n, (tiles_m + 1) / 2 * 2, 1);      // an odd last M tile is all out-of-bounds: zero-filled loads, masked stores
-  cfg.blockDim = dim3(vae::TC_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = vae::TC_SMEM_BYTES;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, vae::gemm_nt_3xtf32_kernel<2>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
-                                 flags));
-  vae::count_launch();
-  return 0;
+  const int cap = vae::tc_cluster_cap();
+  const int mc = (cap >= 4 && tiles_m >= 2 && tiles_n % 2 == 0) ? 4 : (cap >= 2 && tiles_m >= 2) ? 2 : 1;
+  const int cx = mc == 4 ? 2 : 1, cy = mc >= 2 ? 2 : 1;
+  if ((rc = vae::make_operand_map(&tAh, d_Ah, M, K, lda, vae::TC_BM / cx))) return rc;
+  if ((rc = vae::make_operand_map(&tAl, d_Al, M, K, lda, vae::TC_BM / cx))) return rc;
+  if ((rc = vae::make_operand_map(&tBh, d_Bh, N, K, ldb, vae::TC_BN / cy))) return rc;
+  if ((rc = vae::make_operand_map(&tBl, d_Bl, N, K, ldb, vae::TC_BN / cy))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mc == 4) return vae::launch_gemm<4>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
+  if (mc == 2) return vae::launch_gemm<2>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
+  return vae::launch_gemm<1>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
 }
 
 }  // extern "C"

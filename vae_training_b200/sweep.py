@@ -48,8 +48,13 @@ def lpt_partition(costs: List[float], n_parts: int) -> List[List[int]]:
     return parts
 
 
-def run_sweep(all_args, rank=0, world=1, save=True, verbose=False):
+def run_sweep(all_args, rank=0, world=1, save=True, verbose=False, timings=None):
+    import time
+
+    import torch
+
     from .vae import train_many
+    t0 = time.perf_counter()
     mine = lpt_partition([run_cost(a) for a in all_args], world)[rank]
     models = []
     for i in mine:
@@ -57,7 +62,13 @@ def run_sweep(all_args, rank=0, world=1, save=True, verbose=False):
         out_dir = runmod.make_output_dir(a.name, a.overwrite, a) if save else None
         ds = runmod.get_dataset(a.dataset, a.dataset_seed, a.padding_dim, a.batch_size, a)
         models.append(runmod.get_model(a, ds, out_dir, verbose=verbose))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     train_many(models, save=save)
+    torch.cuda.synchronize()
+    if timings is not None:
+        timings["setup_seconds"] = t1 - t0                    # datasets, initial parameters, uploads
+        timings["train_seconds"] = time.perf_counter() - t1   # the training loops incl. eval events
     if save:
         for m in models:
             m.save(final=True)

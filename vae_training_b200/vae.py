@@ -56,7 +56,8 @@ class VAEModel:
         self.latent_dim = latent_dimension if latent_dimension else dataset.dimension   # model.py:128
         self.latent_dimension = latent_dimension
         self.epsilon = epsilon
-        self.stats = defaultdict(list)                            # model.py:35
+        self._stats = defaultdict(list)                           # model.py:35
+        self._pending_stats = defaultdict(list)                   # device scalars not yet read back
         self.average_log_likelihoods = []
         self.epoch_num = 0
         self.batchnum = 0
@@ -168,14 +169,31 @@ class VAEModel:
         stats.update(score)
         return stats
 
+    @property
+    def stats(self):
+        """stat name -> list of floats (model.py:35).  Values recorded by a quiet run stay on the
+        device until somebody looks: reading them back at every event would stall the stream
+        between two persistent launches."""
+        for stat, pend in self._pending_stats.items():
+            if pend:
+                self._stats[stat].extend(torch.stack([p.reshape(()) for p in pend]).cpu().tolist())
+                pend.clear()
+        return self._stats
+
     def write_stats(self, stats):                                  # model.py:195-205
+        if not self.verbose:
+            for stat, val in stats.items():
+                if torch.is_tensor(val) and val.is_cuda:
+                    self._pending_stats[stat].append(val.detach().clone())
+                else:
+                    self.stats[stat].append(float(val))
+            return
         message = f"Batch | {self.batchnum}"
         for stat, val in stats.items():
             val = float(val)
             self.stats[stat].append(val)
             message = message + f" | {stat} | {val:.3f}"
-        if self.verbose:
-            print(message, flush=True)
+        print(message, flush=True)
 
     def plot_epoch(self):                                          # model.py:139-146
         key = self._split_model_key()
@@ -274,26 +292,47 @@ def train_many(models: Sequence[VAEModel], save=True):
     other = [m for m in models if not m.fused]
     for m in models:
         m.begin()
-    # one pack per fused-kernel class (single-CTA models / cluster models)
-    for cls in (1, 2):
-        fused = [m for m in models if m.fused_class == cls]
-        if not fused:
-            continue
-        scratch = ops.fused_scratch(len(fused), fused[0].device)
-        b = 0
-        while True:
-            active = [m for m in fused if b < m.num_batches]
-            if not active:
-                break
-            for m in active:
-                m.events_at(b, save=save)
-            nxt = min(m.next_event(b) for m in active)
-            c = nxt - b
-            ops.train_fused([m._job for m in active], c, scratch)
-            for m in active:
-                m._loss_pieces.append(m._chunk_loss[:c].clone())
-                m.batchnum = nxt
-            b = nxt
+    # One pack per fused-kernel class (single-CTA models / cluster models).  The two packs are
+    # independent serial chains, so they run CONCURRENTLY: one host thread + one CUDA stream per
+    # class (the ctypes calls release the GIL; torch's current stream is thread-local).
+    def run_pack(fused, stream, errors):
+        try:
+            with torch.cuda.stream(stream):
+                scratch = ops.fused_scratch(len(fused), fused[0].device)
+                b = 0
+                while True:
+                    active = [m for m in fused if b < m.num_batches]
+                    if not active:
+                        break
+                    for m in active:
+                        m.events_at(b, save=save)
+                    nxt = min(m.next_event(b) for m in active)
+                    c = nxt - b
+                    ops.train_fused([m._job for m in active], c, scratch)
+                    for m in active:
+                        m._loss_pieces.append(m._chunk_loss[:c].clone())
+                        m.batchnum = nxt
+                    b = nxt
+                stream.synchronize()
+        except BaseException as e:          # re-raised on the caller's thread
+            errors.append(e)
+
+    packs = [[m for m in models if m.fused_class == cls] for cls in (1, 2)]
+    packs = [p for p in packs if p]
+    if packs:
+        import threading
+        dev = packs[0][0].device
+        torch.cuda.current_stream(dev).synchronize()           # state uploads are complete
+        errors, threads = [], []
+        for p_ in packs:
+            st = torch.cuda.Stream(device=dev)
+            th = threading.Thread(target=run_pack, args=(p_, st, errors))
+            th.start()
+            threads.append(th)
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
     for m in other:
         b = 0
         while b < m.num_batches:
