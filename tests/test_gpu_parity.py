@@ -617,7 +617,7 @@ def test_fused_cluster_vs_oracle_loop(ops, lib, case):
 def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
     """Small packs run each model on a 16-CTA (non-portable) cluster, large packs on 8 CTAs
     (fused_mlp.cu:mlp_pick_cluster).  Column slices change, the arithmetic per output element
-    does not: both cluster sizes must agree bit for bit."""
+    does not: both cluster sizes must agree bit for bit (results never depend on the pack size)."""
     n = 10
     out = {}
     for cs in ("8", "16"):
