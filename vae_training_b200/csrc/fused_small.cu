@@ -704,13 +704,26 @@ static SmallPlan plan_small(const VaeTrainJob* job0, int n_jobs, bool homogeneou
   small_shape_of(job0, &fl2, 2);
   p.smem = (size_t)fl1 * 4;
   if (!homogeneous) return p;
-  if (env_cap("VAE_SMALL_GM", kGM, kGM) == kGM && n_jobs % kGM == 0 && job0->desc.batch == kGroupBatch && (size_t)fl1 * 4 * kGM <= (size_t)kMaxSmem) {
+  // models resident per SM under each plan, from the shared-memory footprints (+1 KB the driver
+  // reserves per CTA) and the register cap of the kernels (8 x 128 threads or 2 x 512 threads):
+  // sharing must not cost occupancy -- the big shapes (e.g. D = 28, L = 24: 100 KB per model) keep
+  // one model per CTA and private draws.
+  auto fit = [](size_t bytes, int cap) { const int n = (int)((size_t)kMaxSmem / (bytes + 1024)); return n < cap ? n : cap; };
+  const int per_private = fit((size_t)fl1 * 4, 8);
+  const int per_gm = kGM * fit((size_t)fl1 * 4 * kGM, 8 / kGM > 0 ? 8 / kGM : 1);
+  const int per_cl = fit((size_t)fl2 * 4, 8);
+  int dev = 0, sms = 148;                      // a pack that is fully resident anyway may always share
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError(); sms = 148;
+  }
+  if (env_cap("VAE_SMALL_GM", kGM, kGM) == kGM && n_jobs % kGM == 0 && job0->desc.batch == kGroupBatch &&
+      (size_t)fl1 * 4 * kGM <= (size_t)kMaxSmem && (per_gm >= per_private || n_jobs <= per_gm * sms)) {
     p.gm = kGM; p.smem = (size_t)fl1 * 4 * kGM;
     return p;
   }
-  if (env_cap("VAE_SMALL_CLUSTER", 2, 8) >= 2 && n_jobs % 2 == 0 && (size_t)fl2 * 4 <= (size_t)kMaxSmem) {
+  const int cap = env_cap("VAE_SMALL_CLUSTER", 2, 8);
+  if (cap >= 2 && n_jobs % 2 == 0 && (size_t)fl2 * 4 <= (size_t)kMaxSmem && (per_cl >= per_private || n_jobs <= per_cl * sms)) {
     int c = 2;
-    const int cap = env_cap("VAE_SMALL_CLUSTER", 2, 8);
     while (c * 2 <= cap && n_jobs % (c * 2) == 0) c *= 2;
     p.cluster = c; p.nbuf = 2; p.smem = (size_t)fl2 * 4;
   }
@@ -799,7 +812,7 @@ int small_ctas_per_sm(const VaeTrainJob* job) {
   int fl = 0, out = 0;
   const int id = small_shape_of(job, &fl);
   if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) return 0;
-  const SmallPlan p = plan_small(job, 8 * kGM, true);
+  const SmallPlan p = plan_small(job, 1 << 20, true);        // a pack large enough to fill the GPU
   const int rc = occupancy_small(id, p, &out);
   return rc ? rc : out;
 }
