@@ -97,11 +97,12 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, c
     const bool live = tt < 2 * ntile;
     const int tile = live ? tt >> 1 : ntile - 1, half = tt & 1;
     const int cg = tile / NG, rg = tile - cg * NG;
-    float acc[4][4];
+    // Blackwell packed FP32 FMA (FFMA2): accumulators are row pairs, (a.x, a.y) / (a.z, a.w) are natural
+    // register pairs of the 128-bit load; only the weight has to be duplicated into a pair.  Every lane
+    // of a pair performs the same RN fma as the scalar form: results are unchanged.
+    float2 acc2[4][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc2[j][0] = make_float2(0.f, 0.f); acc2[j][1] = make_float2(0.f, 0.f); }
     const float* ap = AT + 4 * rg;
     const float* wp = Ws + 4 * cg;
     const int kbeg = half ? kh : 0, kend = half ? K : kh;
@@ -109,13 +110,18 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, c
     for (int k = kbeg; k < kend; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(ap + k * BP);
       const float4 wv = *reinterpret_cast<const float4*>(wp + k * W4);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
       const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[j][r] = fmaf(wj[j], av[r], acc[j][r]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 ww = make_float2(wj[j], wj[j]);
+        acc2[j][0] = __ffma2_rn(ww, a01, acc2[j][0]);
+        acc2[j][1] = __ffma2_rn(ww, a23, acc2[j][1]);
+      }
     }
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = acc2[j][0].x; acc[j][1] = acc2[j][0].y; acc[j][2] = acc2[j][1].x; acc[j][3] = acc2[j][1].y; }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -168,11 +174,13 @@ __device__ __forceinline__ void tile_dw(const float* __restrict__ HT, int K, con
     for (int i = 0; i < 4; ++i) hp[i] = HT + (size_t)min(kg + i * KT, K - 1) * BP;
 #pragma unroll
     for (int j = 0; j < 4; ++j) dp[j] = dYT + (size_t)(c0 + min(4 * cg + j, w - 1)) * BP;
-    float acc[4][4];
+    // FFMA2: each accumulator is a pair over the (x, y) / (z, w) halves of the 128-bit batch loads
+    // (even and odd batch columns are summed separately, then added)
+    float2 acc2[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     for (int g = 0; g < NG; ++g) {
       float4 hv[4], dv[4];
 #pragma unroll
@@ -183,12 +191,17 @@ __device__ __forceinline__ void tile_dw(const float* __restrict__ HT, int K, con
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float a = acc[i][j];
-          a = fmaf(hv[i].x, dv[j].x, a); a = fmaf(hv[i].y, dv[j].y, a);
-          a = fmaf(hv[i].z, dv[j].z, a); a = fmaf(hv[i].w, dv[j].w, a);
-          acc[i][j] = a;
+          float2 a = acc2[i][j];
+          a = __ffma2_rn(make_float2(hv[i].x, hv[i].y), make_float2(dv[j].x, dv[j].y), a);
+          a = __ffma2_rn(make_float2(hv[i].z, hv[i].w), make_float2(dv[j].z, dv[j].w), a);
+          acc2[i][j] = a;
         }
     }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = kg + i * KT;
