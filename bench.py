@@ -211,7 +211,7 @@ def run_b200(args):
     else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
         probe = PackedRuns(make_specs(args.workload, 1), max_chunk=4)
         n_models = max(1, ops.fused_resident_jobs(probe.jobs[0]))
-        if n_models >= 8:
+        if n_models >= 8 and not wl_hidden(args.workload):
             n_models -= n_models % 8      # whole CTAs of 4 models / whole cluster pairs (fused_small.cu)
         del probe
     specs = make_specs(args.workload, n_models, first_index=rank * n_models)
