@@ -43,6 +43,8 @@ WORKLOADS = {
     "sphere_dd3_pd3_ld6": ("sphere", 3, 3, 6, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:1", (200, 200, 200)),
     "sphere_dd5_pd16_ld16": ("sphere", 5, 16, 16, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:3", (200, 200, 200)),
 }
+# dram bytes (read + write) of one captured launch of the workload's fused kernel, from profiles/ (ncu --set full)
+NCU_TRAFFIC = {"sigmoid_dd3_pd3_ld6": 2779904 + 68352}
 # BASELINE.json configs[4]: ONE scaled sphere VAE, data-parallel with an NCCL gradient allreduce
 # (D = 512 + 512, width 4096 x 3, batch 65 536, L = 16 -- L is our choice)
 DP_WORKLOADS = {
@@ -334,7 +336,10 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
                          "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
-                         "traffic": None,
+                         "traffic": NCU_TRAFFIC.get(args.workload),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE 2000-step launch of this "
+                                         "kernel (ncu --set full, profiles/r01_fused_small_v4_ncu_full.txt): the job "
+                                         "table + initial state; per-step losses are absorbed by L2 within a launch",
                          "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one "
                                  f"GPU; peak = FFMA probe measured in this run ({ffma_tflops:.1f} TFLOP/s); RNG work "
                                  f"({spec.normals_per_step()} threefry normals/model-step) is not counted as flops",
@@ -472,6 +477,9 @@ def run_dp(args):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
     if args.impl == "reference":
         run_reference(args)
