@@ -125,3 +125,24 @@ def test_builtin_sweeps_match_reference_scripts():
         for k in ref:
             for f in fields:
                 assert getattr(ref[k], f) == getattr(mine[k], f), (which, k, f)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON
+    line with the contract's keys; here on a tiny bounded sample so the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "300", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "train-steps/s" and d["higher_is_better"] is True
+    assert d["metric"] == "vae_train_steps_per_sec_summed_over_packed_models"
+    assert d["steps"] == 300 and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
