@@ -615,12 +615,12 @@ def test_fused_cluster_vs_oracle_loop(ops, lib, case):
 
 
 def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
-    """Small packs run each model on a 16-CTA (non-portable) cluster, large packs on 8 CTAs
+    """Small packs run each model on a 16-CTA (non-portable) cluster, larger packs on 8 or 4 CTAs
     (fused_mlp.cu:mlp_pick_cluster).  Column slices change, the arithmetic per output element
     does not: both cluster sizes must agree bit for bit (results never depend on the pack size)."""
     n = 10
     out = {}
-    for cs in ("8", "16"):
+    for cs in ("4", "8", "16"):
         monkeypatch.setenv("VAE_MLP_CLUSTER", cs)
         res = []
         for case in (MLP_CASES[0], MLP_CASES[2], MLP_CASES[5], MLP_CASES[6]):
@@ -629,9 +629,10 @@ def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
             torch.cuda.synchronize()
             res.append(st)
         out[cs] = res
-    for a, b in zip(out["8"], out["16"]):
-        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
-            assert torch.equal(a[k], b[k]), k
+    for other in ("4", "16"):
+        for a, b in zip(out["8"], out[other]):
+            for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+                assert torch.equal(a[k], b[k]), (other, k)
 
 
 def test_fused_cluster_first_step_gradient_exact_path(ops, lib):

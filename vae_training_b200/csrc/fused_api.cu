@@ -12,11 +12,11 @@ size_t small_job_bytes();
 int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch, cudaStream_t s);
 // fused_mlp.cu
 struct MlpJobDev;
-int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes);
+int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes, size_t* smem4 = nullptr);
 int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o);
 size_t mlp_job_bytes();
-int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s);
-int mlp_resident_jobs(size_t smem, int* out);
+int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_t n_steps, cudaStream_t s);
+int mlp_resident_jobs(size_t smem, size_t smem4, int* out);
 }  // namespace vae
 
 extern "C" {
@@ -49,10 +49,10 @@ int vae_train_fused_resident_jobs(const VaeTrainJob* job) {
     VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     return per_sm * sms;
   }
-  size_t smem = 0;
-  if (!vae::mlp_supported(job, &smem, nullptr)) return 0;
+  size_t smem = 0, smem4 = 0;
+  if (!vae::mlp_supported(job, &smem, nullptr, &smem4)) return 0;
   int out = 0;
-  const int rc = vae::mlp_resident_jobs(smem, &out);
+  const int rc = vae::mlp_resident_jobs(smem, smem4, &out);
   return rc ? rc : out;
 }
 
@@ -84,11 +84,13 @@ int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, vo
   const size_t jb = vae::mlp_job_bytes();
   char* host = (char*)malloc((size_t)n_jobs * jb);
   VAE_REQUIRE(host, "vae_train_fused: out of host memory");
-  size_t smem = 0;
+  size_t smem = 0, smem4 = 0;
+  bool ok4 = true;
   for (int i = 0; i < n_jobs; ++i) {
     const VaeTrainJob& j = jobs[i];
-    size_t sb = 0, wb = 0;
-    vae::mlp_supported(&j, &sb, &wb);
+    size_t sb = 0, wb = 0, s4 = 0;
+    vae::mlp_supported(&j, &sb, &wb, &s4);
+    if (s4 == 0) ok4 = false; else if (s4 > smem4) smem4 = s4;
     if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
         !j.workspace || (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
       free(host);
@@ -103,7 +105,7 @@ int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, vo
   cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * jb, cudaMemcpyHostToDevice, s);
   free(host);
   VAE_CUDA_OK(e);
-  return vae::mlp_launch(d_scratch, n_jobs, smem, n_steps, s);
+  return vae::mlp_launch(d_scratch, n_jobs, smem, ok4 ? smem4 : 0, n_steps, s);
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ constexpr int kMT = 512;                       // threads per CTA
 constexpr int kML = VAE_MAX_HIDDEN + 1;        // max Dense layers per net
 constexpr int kMlpMaxCluster = 8;          // portable cluster size: the throughput configuration
 constexpr int kMlpBigCluster = 16;         // non-portable: one model over 16 SMs (latency configuration)
+constexpr int kMlpSmallCluster = 4;        // packs larger than the resident 8-CTA clusters: more models per GPU
 
 struct MlpJobDev {
   float* params; float* adam_m; float* adam_v; int32_t* step;
@@ -540,7 +541,7 @@ static size_t mlp_ws_floats(const Layout& Lo, const VaeDesc& d, const VaeDataDes
 }
 
 // 2 if the job can run on the cluster kernel, else 0
-int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes) {
+int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes, size_t* smem4) {
   const VaeDesc& d = j->desc;
   const VaeDataDesc& g = j->data;
   if (d.n_enc_hidden + d.n_dec_hidden == 0 || d.sig_decoder) return 0;
@@ -555,6 +556,10 @@ int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes) {
   const size_t sb = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpMaxCluster);
   if (sb > (size_t)227 * 1024 - 2048) return 0;
   if (smem) *smem = sb;
+  if (smem4) {      // 4-CTA clusters stage wider weight slices; 0 if that does not fit
+    const size_t s4 = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpSmallCluster);
+    *smem4 = s4 > (size_t)227 * 1024 - 2048 ? 0 : s4;
+  }
   if (ws_bytes) *ws_bytes = mlp_ws_floats(Lo, d, g, nullptr) * sizeof(float);
   return 2;
 }
@@ -602,22 +607,38 @@ static int mlp_active_clusters(int cs, size_t smem, int* out) {
 }
 
 // clusters (= models) that can be resident at once on the current device (throughput packing)
-int mlp_resident_jobs(size_t smem, int* out) { return mlp_active_clusters(kMlpMaxCluster, smem, out); }
+int mlp_resident_jobs(size_t smem, size_t smem4, int* out) {
+  int f8 = 0, f4 = 0;
+  int rc = mlp_active_clusters(kMlpMaxCluster, smem, &f8);
+  if (rc) return rc;
+  if (smem4 > 0 && mlp_active_clusters(kMlpSmallCluster, smem4, &f4) != 0) { cudaGetLastError(); f4 = 0; }
+  *out = f4 > f8 ? f4 : f8;
+  return 0;
+}
 
 // Cluster size of a launch.  A model's step is a serial chain of 17 cluster-wide phases, so a
 // pack that leaves SMs idle (e.g. the 2 sphere runs per GPU of the 8-GPU sweep) runs each model
-// on 16 CTAs instead of 8: half the GEMM / Adam / staging work per CTA and phase.  Packs that
-// need more than the co-resident 16-CTA clusters keep 8.  VAE_MLP_CLUSTER=8|16 overrides.
-static int mlp_pick_cluster(int n_jobs, size_t smem) {
+// on 16 CTAs: half the GEMM / Adam / staging work per CTA and phase.  Packs that need more than
+// the co-resident 8-CTA clusters use 4 CTAs per model: twice the models per GPU, and the fixed
+// cost of a phase (barrier, operand loads) is paid by half as many CTAs.  All sizes give
+// bit-identical results.  VAE_MLP_CLUSTER=4|8|16 overrides.
+static int mlp_pick_cluster(int n_jobs, size_t smem, size_t smem4) {
   const char* e = getenv("VAE_MLP_CLUSTER");
-  if (e && e[0]) return atoi(e) >= 16 ? kMlpBigCluster : kMlpMaxCluster;
+  if (e && e[0]) {
+    const int v = atoi(e);
+    return v >= 16 ? kMlpBigCluster : (v <= 4 && smem4 > 0) ? kMlpSmallCluster : kMlpMaxCluster;
+  }
   int fit = 0;
-  if (mlp_active_clusters(kMlpBigCluster, smem, &fit) != 0) { cudaGetLastError(); return kMlpMaxCluster; }
-  return n_jobs <= fit ? kMlpBigCluster : kMlpMaxCluster;
+  if (mlp_active_clusters(kMlpBigCluster, smem, &fit) != 0) { cudaGetLastError(); fit = 0; }
+  if (n_jobs <= fit) return kMlpBigCluster;
+  if (smem4 == 0) return kMlpMaxCluster;
+  if (mlp_active_clusters(kMlpMaxCluster, smem, &fit) != 0) { cudaGetLastError(); return kMlpMaxCluster; }
+  return n_jobs <= fit ? kMlpMaxCluster : kMlpSmallCluster;
 }
 
-int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, int64_t n_steps, cudaStream_t s) {
-  const int cs = mlp_pick_cluster(n_jobs, smem);
+int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_t n_steps, cudaStream_t s) {
+  const int cs = mlp_pick_cluster(n_jobs, smem, smem4);
+  if (cs == kMlpSmallCluster) smem = smem4;
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
