@@ -65,6 +65,26 @@ def test_train_schedule_matches_oracle(name, dd, pd, L, hidden):
     compare(m, tr, ods_, N)
 
 
+def test_dataset_noise_takes_the_per_op_path():
+    """`-dn` / var_added > 0 (datasets.py:189-192) draws a second key and adds noise to every batch:
+    the fused kernels do not model it, so such a run must fall back to the per-op step and still
+    follow the oracle's schedule (loss, key chains, stats)."""
+    from vae_training_b200 import datasets, vae
+    N, seed, dd, pd, L = 12, 2, 3, 9, 20
+    ds = datasets.LinearGaussianDataset(seed, dimension=dd, intrinsic_dimension=3, padding_dimension=pd, var_added=0.25)
+    ods_ = ods.make_dataset("linear_gaussian", seed, dd, pd, var_added=0.25)
+    d = vs.VaeDesc(100, ods_.ndim, L, [], [], epsilon0=-1.0, lr=1e-3)
+    flat = vs.init_params(d, 0)
+    m = vae.VAEModel(None, N, 1, 100, 1e-3, "", "", None, None, -1.0, False, ds, L, tunable_decoder_var=True,
+                     dataset_name="linear_gaussian", initial_params=flat, verbose=False)
+    assert not m.fused and m.fused_class == 0
+    m.n_print, m.n_plot, m.print_batch_size, m.plot_batch_size = 4, 8, 50, 50
+    tr = otr.OracleTrainer(d, ods_, flat, n_print=4, n_plot=8, eval_batch=50, dtype=np.float64)
+    m.train_distribution(save=False)
+    tr.train(N)
+    compare(m, tr, ods_, N)
+
+
 def test_train_many_equals_individual_runs():
     from vae_training_b200 import vae
     cfgs = [("sigmoid", 3, 3, 6, "", 30), ("sigmoid", 5, 5, 10, "", 22), ("linear_gaussian", 6, 6, 20, "", 17)]

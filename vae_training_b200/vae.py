@@ -91,6 +91,8 @@ class VAEModel:
         self._job = ops.make_job(self.desc, dataset.data_desc(), self.params, self.adam_m, self.adam_v, self.step,
                                  self.key, dataset.key, dataset.A, self._chunk_loss)
         self.fused_class = ops.fused_supported(self._job)
+        if getattr(dataset, "var_added", 0.0) > 0:      # -dn noise (datasets.py:189-192) exists only in the per-op generator
+            self.fused_class = 0
         self.fused = self.fused_class > 0
         self._fused_ws = ops.fused_workspace(self._job, device) if self.fused else None
         if self._fused_ws is not None:
