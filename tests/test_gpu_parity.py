@@ -620,7 +620,7 @@ def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
     does not: both cluster sizes must agree bit for bit (results never depend on the pack size)."""
     n = 10
     out = {}
-    for cs in ("4", "8", "16"):
+    for cs in ("1", "2", "4", "8", "16"):
         monkeypatch.setenv("VAE_MLP_CLUSTER", cs)
         res = []
         for case in (MLP_CASES[0], MLP_CASES[2], MLP_CASES[5], MLP_CASES[6]):
@@ -629,7 +629,7 @@ def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
             torch.cuda.synchronize()
             res.append(st)
         out[cs] = res
-    for other in ("4", "16"):
+    for other in ("1", "2", "4", "16"):
         for a, b in zip(out["8"], out[other]):
             for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
                 assert torch.equal(a[k], b[k]), (other, k)

@@ -27,6 +27,7 @@ constexpr int kMT = 512;                       // threads per CTA
 constexpr int kML = VAE_MAX_HIDDEN + 1;        // max Dense layers per net
 constexpr int kMlpMaxCluster = 8;          // portable cluster size: the throughput configuration
 constexpr int kMlpBigCluster = 16;         // non-portable: one model over 16 SMs (latency configuration)
+constexpr int kMlpMinSlices = 4;           // a layer is cut into at least this many column slices (staging-buffer width)
 constexpr int kMlpSmallCluster = 4;        // packs larger than the resident 8-CTA clusters: more models per GPU
 
 struct MlpJobDev {
@@ -288,7 +289,10 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   }
   __syncthreads();
   const int B = J.B, BP = J.BP, D = J.D, L = J.L, DR = J.DR, G = J.G, LD = L + D;
-  const int W4max = m_up4((J.maxw + CS - 1) / CS);
+  // Column slices per layer: one per CTA, but never fewer than kMlpMinSlices -- clusters of 1 or 2 CTAs
+  // (throughput packs) walk their slices in NP passes through the same staging buffer.
+  const int SL = CS < kMlpMinSlices ? kMlpMinSlices : CS, NP = SL / CS;
+  const int W4max = m_up4((J.maxw + SL - 1) / SL);
   // shared memory carve-up (floats)
   float* bufA = sm;                               // [maxw][BP]  layer input (H^T)
   float* bufB = bufA + (size_t)J.maxw * BP;       // [maxw][BP]  layer output gradient (dY^T)
@@ -377,13 +381,16 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
     // ================= encoder forward
     for (int i = 0; i < J.n_enc; ++i) {
       const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
-      const Slice sc = slice_of(N, rank, CS);
-      const int W4 = m_up4(sc.w);
       const float* AT = xT;
       if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); AT = bufA; }
-      stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
-      cp_async_wait_all(); __syncthreads();
-      tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
+      for (int p = 0; p < NP; ++p) {
+        const Slice sc = slice_of(N, rank + p * CS, SL);
+        const int W4 = m_up4(sc.w);
+        if (p > 0) __syncthreads();                              // the previous pass has finished with Ws
+        stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
+        cp_async_wait_all(); __syncthreads();
+        tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
+      }
       cluster_barrier();
     }
     // ---- reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
@@ -397,13 +404,16 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
     // ================= decoder forward
     for (int i = 0; i < J.n_dec; ++i) {
       const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
-      const Slice sc = slice_of(N, rank, CS);
-      const int W4 = m_up4(sc.w);
       const float* AT = zsT;
       if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); AT = bufA; }
-      stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
-      cp_async_wait_all(); __syncthreads();
-      tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
+      for (int p = 0; p < NP; ++p) {
+        const Slice sc = slice_of(N, rank + p * CS, SL);
+        const int W4 = m_up4(sc.w);
+        if (p > 0) __syncthreads();
+        stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
+        cp_async_wait_all(); __syncthreads();
+        tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
+      }
       cluster_barrier();
     }
     // ================= output, loss, d x_hat (every CTA, all rows; reductions used by CTA 0)
@@ -449,21 +459,29 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
       const float* HT = zsT;
       if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); HT = bufA; }
-      // dX slice: rows k0..k0+kw of the layer input
-      const Slice sk = slice_of(K, rank, CS);
-      const int K4 = m_up4(sk.w);
-      stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
-      cp_async_wait_all(); __syncthreads();
+      // dX slices: rows k0..k0+kw of the layer input
       float* dst = i > 0 ? ws + J.ws_g[pp] : ws + J.ws_dzs;
-      tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
+      for (int p = 0; p < NP; ++p) {
+        const Slice sk = slice_of(K, rank + p * CS, SL);
+        const int K4 = m_up4(sk.w);
+        if (p > 0) __syncthreads();
+        stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
+        cp_async_wait_all(); __syncthreads();
+        tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
+      }
       __syncthreads();
-      // dW slice: columns c0..c0+w of the layer output
-      const Slice sc = slice_of(N, rank, CS);
-      const int W4 = m_up4(sc.w);
-      if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
-      cluster_barrier();
-      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
-      adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+      // dW slices: columns c0..c0+w of the layer output.  Adam may only start once every CTA has
+      // finished reading this layer's weights (the barrier); the first slice's dW is formed before it.
+      for (int p = 0; p < NP; ++p) {
+        const Slice sc = slice_of(N, rank + p * CS, SL);
+        const int W4 = m_up4(sc.w);
+        if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+        if (p == 0) cluster_barrier(); else __syncthreads();
+        if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
+        adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+        if (NP > 1) __syncthreads();
+      }
+      if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }       // bufB was still this layer's dY^T
       cp_async_wait_all(); __syncthreads();
     }
     // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
@@ -490,19 +508,26 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       const float* HT = xT;
       if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); HT = bufA; }
       if (i > 0) {
-        const Slice sk = slice_of(K, rank, CS);
-        const int K4 = m_up4(sk.w);
-        stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
-        cp_async_wait_all(); __syncthreads();
-        tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
+        for (int p = 0; p < NP; ++p) {
+          const Slice sk = slice_of(K, rank + p * CS, SL);
+          const int K4 = m_up4(sk.w);
+          if (p > 0) __syncthreads();
+          stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
+          cp_async_wait_all(); __syncthreads();
+          tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
+        }
         __syncthreads();
       }
-      const Slice sc = slice_of(N, rank, CS);
-      const int W4 = m_up4(sc.w);
-      if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
-      if (i > 0) cluster_barrier(); else __syncthreads();
-      if (i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
-      adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+      for (int p = 0; p < NP; ++p) {
+        const Slice sc = slice_of(N, rank + p * CS, SL);
+        const int W4 = m_up4(sc.w);
+        if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+        if (p == 0 && i > 0) cluster_barrier(); else __syncthreads();
+        if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
+        adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+        if (NP > 1) __syncthreads();
+      }
+      if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
       cp_async_wait_all(); __syncthreads();
     }
     // the next step's phase-R barrier orders this step's parameter writes before any read
@@ -611,7 +636,12 @@ int mlp_resident_jobs(size_t smem, size_t smem4, int* out) {
   int f8 = 0, f4 = 0;
   int rc = mlp_active_clusters(kMlpMaxCluster, smem, &f8);
   if (rc) return rc;
-  if (smem4 > 0 && mlp_active_clusters(kMlpSmallCluster, smem4, &f4) != 0) { cudaGetLastError(); f4 = 0; }
+  if (smem4 > 0)      // 1 CTA per model: the largest pack that is resident at once
+    for (int cs = 4; cs >= 1; cs >>= 1) {
+      int f = 0;
+      if (mlp_active_clusters(cs, smem4, &f) != 0) { cudaGetLastError(); f = 0; }
+      if (f > f4) f4 = f;
+    }
   *out = f4 > f8 ? f4 : f8;
   return 0;
 }
@@ -626,19 +656,26 @@ static int mlp_pick_cluster(int n_jobs, size_t smem, size_t smem4) {
   const char* e = getenv("VAE_MLP_CLUSTER");
   if (e && e[0]) {
     const int v = atoi(e);
-    return v >= 16 ? kMlpBigCluster : (v <= 4 && smem4 > 0) ? kMlpSmallCluster : kMlpMaxCluster;
+    if (v >= 16) return kMlpBigCluster;
+    if (v >= 8 || smem4 == 0) return kMlpMaxCluster;
+    return v >= 4 ? 4 : v >= 2 ? 2 : 1;
   }
   int fit = 0;
   if (mlp_active_clusters(kMlpBigCluster, smem, &fit) != 0) { cudaGetLastError(); fit = 0; }
   if (n_jobs <= fit) return kMlpBigCluster;
   if (smem4 == 0) return kMlpMaxCluster;
   if (mlp_active_clusters(kMlpMaxCluster, smem, &fit) != 0) { cudaGetLastError(); return kMlpMaxCluster; }
-  return n_jobs <= fit ? kMlpMaxCluster : kMlpSmallCluster;
+  if (n_jobs <= fit) return kMlpMaxCluster;
+  for (int cs = 4; cs > 1; cs >>= 1) {        // fewer CTAs per model = more models resident at once
+    if (mlp_active_clusters(cs, smem4, &fit) != 0) { cudaGetLastError(); return kMlpSmallCluster; }
+    if (n_jobs <= fit) return cs;
+  }
+  return 1;
 }
 
 int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_t n_steps, cudaStream_t s) {
   const int cs = mlp_pick_cluster(n_jobs, smem, smem4);
-  if (cs == kMlpSmallCluster) smem = smem4;
+  if (cs <= kMlpSmallCluster) smem = smem4;
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -649,7 +686,7 @@ int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = cs > 1 ? 1 : 0;
   VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)d_jobs, n_steps));
   count_launch();
   return 0;
