@@ -4,8 +4,11 @@
 //
 // The same hot-loop body as fused_small.cu (model.py:221-222: key splits, eps draw, dataset
 // batch, VAE.apply networks.py:61-84, sampled ELBO :94-98, hand-derived backward, legacy flax
-// Adam), but a 166-176k-parameter model (2 MB with Adam state) does not fit one SM.  The
-// cluster's CS CTAs split every Dense layer by OUTPUT COLUMNS:
+// Adam), but a 166-176k-parameter model (2 MB with Adam state) does not fit one SM.  A model
+// runs on a cluster of CS = 16 / 8 / 4 / 2 / 1 CTAs, chosen per launch from the pack size
+// (mlp_pick_cluster: few models -> many CTAs each for latency, many models -> few CTAs each for
+// throughput; results are bit-identical for every CS).  The CTAs split every Dense layer by
+// OUTPUT COLUMNS (at least four slices per layer; CS < 4 walks its slices in passes):
 //   forward   Y[:, slice]  = act(X W[:, slice] + b[slice])              X: all rows, all K
 //   backward  dW[:, slice] = X^T dY[:, slice]  (+ Adam on the slice)     the CTA owns its columns
 //             dX[:, kslice] = (dY W[kslice, :]^T) * relu'(X[:, kslice])   dY: all rows, all N

@@ -1,8 +1,9 @@
 // fused_small.cu -- persistent fused training loop for the single-Dense VAEs of the
 // linear / sigmoid sweeps (seed_linpadding_expts.sh, sigmoid_vae_padding_expts.sh).
 //
-// One CTA (128 threads) owns one model for n_steps consecutive steps.  Everything the
-// reference does per iteration of the hot loop (model.py:221-222) happens on-chip:
+// 128 threads own one model for n_steps consecutive steps; a CTA holds one model (heterogeneous
+// packs, fallback) or four (homogeneous packs: 512 threads, see "Shared eps draw" below).
+// Everything the reference does per iteration of the hot loop (model.py:221-222) happens on-chip:
 //   key splits (vae.py:125, datasets.py:51) -> eps = normal(key,(B,L+D)) (model.py:227)
 //   -> dataset batch (datasets.py:183-195 / 240-249 / 75-84) -> VAE.apply
 //   (networks.py:61-84) -> sampled ELBO (networks.py:94-98) -> hand-derived backward
@@ -15,8 +16,10 @@
 // zero moments) bit-for-bit unchanged; those rows are never loaded.
 //
 // Per step (two CTA barriers):
-//   phase A (all threads)        threefry blocks -> normals -> eps (B, L+D) and generator
-//                                normals (B, g) in smem; lanes 0-3 advance the key chains
+//   phase A (small_draw)         threefry blocks -> normals -> eps (B, L+D) and generator
+//                                normals (B, g) in smem; lanes 0-3 advance the key chains;
+//                                models of a CTA (or of a 2-CTA cluster) that hold equal model
+//                                keys split the eps draw between them
 //   phase B (thread per row)     generator transform, forward, loss partials, backward to
 //                                dmu; operands of the weight gradients are stored
 //                                TRANSPOSED ([feature][batch], batch contiguous)
