@@ -135,3 +135,29 @@ def test_dataset_classes_follow_reference_interface():
     ref2 = ods.LinearGaussianDataset(2, 3, 3, 2, var_added=0.25)
     np.testing.assert_allclose(noisy.get_batch(50).cpu().numpy(), ref2.get_batch(50), rtol=1e-6, atol=1e-7)
     np.testing.assert_array_equal(noisy.key.cpu().numpy(), ref2.key)
+
+
+def test_bench_b200_arm_contract():
+    """`bench.py` (GPU arm) prints ONE JSON line carrying every key of the measurement contract;
+    short run, CPU baseline included on a 1-second sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "300", "--warmup", "3", "--cpu-seconds", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["steps"] == 300 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["gpu_launches"] == 1                                   # one persistent launch in the timed region
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "workload" in d["config"] and "model" not in d["config"]
