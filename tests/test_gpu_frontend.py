@@ -161,3 +161,37 @@ def test_bench_b200_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_all_54_sweep_runs_short_match_oracle(monkeypatch):
+    """BASELINE configs[3]: every run of the three sweep scripts (54 runs: 13 single-Dense shapes, 5
+    hidden-layer shapes, 3 dataset seeds each), built through the run.py flag surface and trained
+    packed by `train_many` -- here for 11 steps with the event cadence shrunk to 5 / 10 -- must follow
+    the oracle trainer run by run: interleaved train / eval losses rel 1e-5, key chains bit-exact,
+    learned variances and stats."""
+    from vae_training_b200 import run, sweep, vae
+    N = 11
+    monkeypatch.setattr(vae.VAEModel, "n_print", 5)
+    monkeypatch.setattr(vae.VAEModel, "n_plot", 10)
+    monkeypatch.setattr(vae.VAEModel, "print_batch_size", 60)
+    monkeypatch.setattr(vae.VAEModel, "plot_batch_size", 60)
+    all_args = sweep.builtin_runs("all", N)
+    assert len(all_args) == 54
+    models, trainers = [], []
+    for a in all_args:
+        ds = run.get_dataset(a.dataset, a.dataset_seed, a.padding_dim, a.batch_size, a)
+        m = run.get_model(a, ds, None, verbose=False)
+        ods_ = ods.make_dataset(a.dataset, a.dataset_seed, a.dataset_dimension, a.padding_dim)
+        hid = [int(v) for v in a.layer_sizes.split("|")] if a.layer_sizes else []
+        d = vs.VaeDesc(a.batch_size, ods_.ndim, a.latent_dimension, hid, hid, sig_decoder=(a.dataset == "sigmoid"),
+                       epsilon0=a.epsilon, lr=a.learning_rate)
+        flat = m.params.cpu().numpy().copy()
+        assert flat.shape == (d.n_params,)
+        tr = otr.OracleTrainer(d, ods_, flat, n_print=5, n_plot=10, eval_batch=60, dtype=np.float64)
+        models.append(m)
+        trainers.append((tr, ods_))
+    assert sorted({m.fused_class for m in models}) == [1, 2]
+    vae.train_many(models, save=False)
+    for m, (tr, ods_) in zip(models, trainers):
+        tr.train(N)
+        compare(m, tr, ods_, N)
