@@ -12,7 +12,7 @@
 // i.e. three tcgen05.mma.kind::tf32 per k-step.  Only algorithmic flops (2MNK) are ever
 // reported as useful work.
 //
-// Structure (one 128x128 output tile per CTA, 192 threads):
+// Structure (persistent: a CTA -- or a cluster of 2 / 4 -- walks 128x128 output tiles; 192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes of 128 rows x 32 floats)
 //               of Ah, Al, Bh, Bl into a 3-stage smem ring, mbarrier expect_tx
 //   warp 1      MMA issuer: one elected lane issues 4 k-steps x 3 terms of
@@ -102,7 +102,7 @@ __host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
 //   * the two correction terms (2^-11 of the magnitude) accumulate over all of K in a third
 //     accumulator -- their truncation bias is 2^-11 of the above and negligible.
 constexpr int TC_CHUNK = 8;                     // k-blocks per main-accumulator chunk
-constexpr int TC_TMEM_COLS = 512;               // main0 | main1 | small | (unused)
+constexpr int TC_TMEM_COLS = 512;               // main0 | main1 | small0 | small1
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -128,22 +128,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // same way (32 KB per k-block per CTA).  Cluster rank = cx + CX * cy (cx along N, cy along M).
 // A stage may be refilled only when EVERY CTA that reads what this CTA multicasts has consumed it:
 // tcgen05.commit arrives on the empty barrier of this CTA and of its row / column partners.
+// PERSISTENT: one cluster per SM group walks the output tiles (cluster tile ct = cn + ctn * cm, n
+// fastest) with the shared-memory ring, the main-accumulator ping-pong and a double-buffered
+// correction accumulator all running ACROSS tiles: the TMA producer and the MMA issuer start tile
+// t+1 while the epilogue warps still drain / store tile t, so neither the pipeline fill nor the
+// epilogue is exposed per tile.  TMEM (512 columns): main0 | main1 | small0 | small1.
 template <int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       float* __restrict__ C, int M, int N, int K, int64_t ldc, const float* __restrict__ bias,
-                      const float* __restrict__ mask, int64_t ldm, int flags) {
+                      const float* __restrict__ mask, int64_t ldm, int flags, int ctn, int n_ctiles) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t mfull_bar[2];     // main accumulator chunk complete
   __shared__ __align__(8) uint64_t mempty_bar[2];    // main accumulator drained (4 epilogue warps)
-  __shared__ __align__(8) uint64_t acc_bar;          // every MMA of the tile complete
+  __shared__ __align__(8) uint64_t sfull_bar[2];     // every MMA of a tile complete (its correction accumulator is final)
+  __shared__ __align__(8) uint64_t sempty_bar[2];    // correction accumulator drained (4 epilogue warps)
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int nchunk = (nkb + TC_CHUNK - 1) / TC_CHUNK;
   constexpr int CX = MC == 4 ? 2 : 1, CY = MC >= 2 ? 2 : 1;         // cluster extent along N / along M
@@ -153,6 +158,13 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const uint16_t a_mask = (uint16_t)(((1u << CX) - 1u) << (cy * CX));
   const uint16_t b_mask = (uint16_t)((1u << cx) | (CY > 1 ? 1u << (cx + CX) : 0u));
   const uint16_t peers_mask = (uint16_t)(a_mask | b_mask);
+  const int cluster_id = (int)blockIdx.x / MC, n_clusters = (int)gridDim.x / MC;
+  // this CTA's tile of cluster tile ct
+  auto tile_of = [&](int ct, int& m0, int& n0) {
+    const int cn = ct % ctn, cm = ct / ctn;
+    n0 = (cn * CX + (int)cx) * TC_BN;
+    m0 = (cm * CY + (int)cy) * TC_BM;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAh)));
@@ -162,8 +174,10 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CX + CY - 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&mfull_bar[b], 1); mbar_init(&mempty_bar[b], 4); }
-    mbar_init(&acc_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&mfull_bar[b], 1); mbar_init(&mempty_bar[b], 4);
+      mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // one warp allocates the tensor memory (power of two >= 32 columns) and owns the dealloc
@@ -180,29 +194,34 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);                 // slot free (first pass: immediately)
-        uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
-        if (CX == 1) {
-          tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
-          tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
-        } else {      // this CTA's half of the A rows, multicast to the CTAs with the same M tile
-          const int half_rows = TC_BM / CX;
-          const size_t off = (size_t)cx * half_rows * TC_BK * 4;
-          tma_load_2d_mc(st + 0 * TC_TILE_BYTES + off, &tmAh, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
-          tma_load_2d_mc(st + 1 * TC_TILE_BYTES + off, &tmAl, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
-        }
-        if (CY == 1) {
-          tma_load_2d(st + 2 * TC_TILE_BYTES, &tmBh, &full_bar[s], kb * TC_BK, n0);
-          tma_load_2d(st + 3 * TC_TILE_BYTES, &tmBl, &full_bar[s], kb * TC_BK, n0);
-        } else {      // this CTA's half of the B rows, multicast to the CTAs with the same N tile
-          const int half_rows = TC_BN / CY;
-          const size_t off = (size_t)cy * half_rows * TC_BK * 4;
-          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
-          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
+      uint32_t it = 0;                                       // k-blocks issued so far, across tiles
+      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+        int m0, n0;
+        tile_of(ct, m0, n0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % TC_STAGES);
+          const uint32_t ph = (it / TC_STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);                 // slot free (first pass: immediately)
+          uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
+          if (CX == 1) {
+            tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
+            tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
+          } else {      // this CTA's half of the A rows, multicast to the CTAs with the same M tile
+            const int half_rows = TC_BM / CX;
+            const size_t off = (size_t)cx * half_rows * TC_BK * 4;
+            tma_load_2d_mc(st + 0 * TC_TILE_BYTES + off, &tmAh, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
+            tma_load_2d_mc(st + 1 * TC_TILE_BYTES + off, &tmAl, &full_bar[s], kb * TC_BK, m0 + (int)cx * half_rows, a_mask);
+          }
+          if (CY == 1) {
+            tma_load_2d(st + 2 * TC_TILE_BYTES, &tmBh, &full_bar[s], kb * TC_BK, n0);
+            tma_load_2d(st + 3 * TC_TILE_BYTES, &tmBl, &full_bar[s], kb * TC_BK, n0);
+          } else {      // this CTA's half of the B rows, multicast to the CTAs with the same N tile
+            const int half_rows = TC_BN / CY;
+            const size_t off = (size_t)cy * half_rows * TC_BK * 4;
+            tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
+            tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
+          }
         }
       }
     }
@@ -210,87 +229,105 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     // ===================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        const int chunk = kb / TC_CHUNK, buf = chunk & 1;
-        const bool first = (kb % TC_CHUNK) == 0;
-        if (first) {                                        // the drain of this buffer's previous chunk is done
-          mbar_wait(&mempty_bar[buf], (uint32_t)((chunk >> 1) & 1) ^ 1u);
-          tc_fence_after();
-        }
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, gc = 0, t = 0;                        // k-blocks, main chunks, tiles so far
+      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++t) {
+        const uint32_t sb = t & 1u;
+        mbar_wait(&sempty_bar[sb], ((t >> 1) & 1u) ^ 1u);    // correction accumulator sb drained (tile t - 2)
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-        const uint64_t dAh = make_kmajor_sw128_desc(base + 0 * TC_TILE_BYTES), dAl = make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
-        const uint64_t dBh = make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES), dBl = make_kmajor_sw128_desc(base + 3 * TC_TILE_BYTES);
-        const uint32_t tmem_main = tmem_acc + (uint32_t)(buf * TC_BN);
+        const uint32_t tmem_sm = tmem_small + sb * TC_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % TC_STAGES);
+          const uint32_t ph = (it / TC_STAGES) & 1u;
+          const uint32_t buf = gc & 1u;
+          const bool first = (kb % TC_CHUNK) == 0;
+          if (first) {                                        // the drain of this buffer's previous chunk is done
+            mbar_wait(&mempty_bar[buf], ((gc >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+          const uint64_t dAh = make_kmajor_sw128_desc(base + 0 * TC_TILE_BYTES), dAl = make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
+          const uint64_t dBh = make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES), dBl = make_kmajor_sw128_desc(base + 3 * TC_TILE_BYTES);
+          const uint32_t tmem_main = tmem_acc + buf * TC_BN;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // +32 bytes per K=8 step inside the 128-byte row
-          umma_tf32(tmem_main, dAh + adv, dBh + adv, idesc, !(first && k == 0));
-          umma_tf32(tmem_small, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
-          umma_tf32(tmem_small, dAl + adv, dBh + adv, idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // +32 bytes per K=8 step inside the 128-byte row
+            umma_tf32(tmem_main, dAh + adv, dBh + adv, idesc, !(first && k == 0));
+            umma_tf32(tmem_sm, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
+            umma_tf32(tmem_sm, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
+          else umma_commit_mc(&empty_bar[s], peers_mask);
+          if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) { umma_commit(&mfull_bar[buf]); ++gc; }
         }
-        if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
-        else umma_commit_mc(&empty_bar[s], peers_mask);
-        if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) umma_commit(&mfull_bar[buf]);
+        umma_commit(&sfull_bar[sb]);                         // every MMA of the tile complete
       }
-      umma_commit(&acc_bar);                               // every MMA of the tile complete
     }
   } else {
     // ===================== epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float acc[TC_BN];
+    uint32_t gc = 0, t = 0;
+    for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++t) {
+      int m0, n0;
+      tile_of(ct, m0, n0);
+      const int row = m0 + q * 32 + lane;
+      float acc[TC_BN];
 #pragma unroll
-    for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
-    for (int chunk = 0; chunk < nchunk; ++chunk) {
-      const int buf = chunk & 1;
-      mbar_wait(&mfull_bar[buf], (uint32_t)((chunk >> 1) & 1));
+      for (int j = 0; j < TC_BN; ++j) acc[j] = 0.f;
+      for (int chunk = 0; chunk < nchunk; ++chunk, ++gc) {
+        const uint32_t buf = gc & 1u;
+        mbar_wait(&mfull_bar[buf], (gc >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + lane_off + (uint32_t)(buf * TC_BN + c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mempty_bar[buf]);
+      }
+      const uint32_t sb = t & 1u;
+      mbar_wait(&sfull_bar[sb], (t >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < TC_BN / 32; ++c) {
         uint32_t v[32];
-        tmem_ld32(tmem_acc + lane_off + (uint32_t)(buf * TC_BN + c * 32), v);
+        tmem_ld32(tmem_small + lane_off + (uint32_t)(sb * TC_BN + c * 32), v);
+        if (c == TC_BN / 32 - 1) {                           // correction accumulator fully read: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sempty_bar[sb]);
+        }
+        if (row < M) {
+          const int nb = n0 + c * 32;
+          float* crow = C + (int64_t)row * ldc + nb;
+          const float* mrow = (flags & TC_MASK) ? mask + (int64_t)row * ldm + nb : nullptr;
+          const bool vec = (nb + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mempty_bar[buf]);
-    }
-    mbar_wait(&acc_bar, 0u);
-    tc_fence_after();
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
 #pragma unroll
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_small + lane_off + (uint32_t)(c * 32), v);
-      if (row < M) {
-        const int nb = n0 + c * 32;
-        float* crow = C + (int64_t)row * ldc + nb;
-        const float* mrow = (flags & TC_MASK) ? mask + (int64_t)row * ldm + nb : nullptr;
-        const bool vec = (nb + 32 <= N) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float x = acc[c * 32 + j + u] + __uint_as_float(v[j + u]);
-            if (nb + j + u < N) {
-              if (flags & TC_BIAS) x += bias[nb + j + u];
-              if (flags & TC_RELU) x = fmaxf(x, 0.f);
-              if (flags & TC_MASK) x = mrow[j + u] > 0.f ? x : 0.f;
+            for (int u = 0; u < 4; ++u) {
+              float x = acc[c * 32 + j + u] + __uint_as_float(v[j + u]);
+              if (nb + j + u < N) {
+                if (flags & TC_BIAS) x += bias[nb + j + u];
+                if (flags & TC_RELU) x = fmaxf(x, 0.f);
+                if (flags & TC_MASK) x = mrow[j + u] > 0.f ? x : 0.f;
+              }
+              o[u] = x;
             }
-            o[u] = x;
-          }
-          if (vec) {
-            *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+            if (vec) {
+              *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (nb + j + u < N) crow[j + u] = o[u];
+              for (int u = 0; u < 4; ++u)
+                if (nb + j + u < N) crow[j + u] = o[u];
+            }
           }
         }
       }
@@ -394,18 +431,27 @@ static int launch_gemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUt
                        int flags, int tiles_n, int tiles_m, cudaStream_t stream) {
   constexpr int CX = MC == 4 ? 2 : 1, CY = MC >= 2 ? 2 : 1;
   VAE_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  // cluster tiles: ctn along N, ctm along M (an odd last M tile of a pair is all out-of-bounds: zero-filled
+  // loads, masked stores); the persistent grid is one cluster per MC SMs, or fewer if there are fewer tiles
+  const int ctn = tiles_n / CX, ctm = (tiles_m + CY - 1) / CY;
+  const int n_ctiles = ctn * ctm;
+  int dev = 0, sms = 148;
+  VAE_CUDA_OK(cudaGetDevice(&dev));
+  VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int n_clusters = sms / MC;
+  if (n_clusters > n_ctiles) n_clusters = n_ctiles;
+  if (n_clusters < 1) n_clusters = 1;
   cudaLaunchConfig_t cfg = {};
-  // an odd last M tile is all out-of-bounds: zero-filled loads, masked stores
-  cfg.gridDim = dim3(tiles_n, (tiles_m + CY - 1) / CY * CY, 1);
+  cfg.gridDim = dim3(n_clusters * MC, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CX; attr[0].val.clusterDim.y = CY; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = MC > 1 ? 1 : 0;
   VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_nt_3xtf32_kernel<MC>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
-                                 flags));
+                                 flags, ctn, n_ctiles));
   count_launch();
   return 0;
 }
