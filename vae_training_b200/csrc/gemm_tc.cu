@@ -32,6 +32,7 @@ constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;             // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;            // Ah Al Bh Bl
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;
 constexpr int TC_THREADS = 192;
+constexpr int TC_GROUP_M = 8;                                // cluster tiles along M per rasterisation group
 enum { TC_BIAS = 1, TC_RELU = 2, TC_MASK = 4 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,8 +161,14 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const uint16_t peers_mask = (uint16_t)(a_mask | b_mask);
   const int cluster_id = (int)blockIdx.x / MC, n_clusters = (int)gridDim.x / MC;
   // this CTA's tile of cluster tile ct
+  // Grouped rasterisation: consecutive cluster tiles walk TC_GROUP_M tiles down M before moving one
+  // tile along N, so the clusters that run at the same time share a near-square set of A / B panels
+  // (less DRAM traffic per wave than sweeping all of N for two M tiles).
+  const int ctm = n_ctiles / ctn;
   auto tile_of = [&](int ct, int& m0, int& n0) {
-    const int cn = ct % ctn, cm = ct / ctn;
+    const int gsz_full = TC_GROUP_M * ctn, grp = ct / gsz_full, rem = ct - grp * gsz_full;
+    const int first_m = grp * TC_GROUP_M, gm = min(ctm - first_m, TC_GROUP_M);
+    const int cm = first_m + rem % gm, cn = rem / gm;
     n0 = (cn * CX + (int)cx) * TC_BN;
     m0 = (cm * CY + (int)cy) * TC_BM;
   };
