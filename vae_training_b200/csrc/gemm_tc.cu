@@ -9,8 +9,10 @@
 // to nearest; hi + lo reproduces X to ~2^-23), and the product is accumulated in FP32 in
 // tensor memory as
 //   A*B ~= Ah*Bh + Ah*Bl + Al*Bh         (the dropped Al*Bl term is ~2^-22 relative)
-// i.e. three tcgen05.mma.kind::tf32 per k-step.  Only algorithmic flops (2MNK) are ever
-// reported as useful work.
+// i.e. three M128 N128 K8 products per k-step, issued as TWO tcgen05.mma.kind::tf32: Ah * [Bh ; Bl]^T
+// as one N = 256 MMA (Bh and Bl are adjacent in the stage, so one descriptor spans both: Ah is read
+// from shared memory once, not twice -- the kernel is shared-memory-bandwidth bound) and Al * Bh^T.
+// Only algorithmic flops (2MNK) are ever reported as useful work.
 //
 // Structure (persistent: a CTA -- or a cluster of 2 / 4 -- walks 128x128 output tiles; 192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes of 128 rows x 32 floats)
@@ -96,14 +98,14 @@ __host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
 // The tensor core accumulates in FP32 with round-toward-zero: a long accumulation chain in
 // TMEM picks up a systematic bias that grows linearly with K (measured: 2.5e-5 relative at
 // K = 4096).  Two-level accumulation keeps FP32-level accuracy:
-//   * the dominant term Ah*Bh goes to one of two 128-column "main" accumulators in chunks of
-//     TC_CHUNK k-blocks (K = 256: 32 tensor-core accumulations); each finished chunk is drained
-//     by the epilogue warps into FP32 registers (round-to-nearest adds) while the tensor core
-//     fills the other buffer;
-//   * the two correction terms (2^-11 of the magnitude) accumulate over all of K in a third
-//     accumulator -- their truncation bias is 2^-11 of the above and negligible.
+//   * TMEM holds two 256-column buffers (main | correction columns); a buffer accumulates a chunk of
+//     TC_CHUNK k-blocks (K = 256: 32 tensor-core accumulations), then the epilogue warps drain it
+//     into FP32 registers (round-to-nearest adds of main + correction) while the tensor core fills
+//     the other buffer;
+//   * the correction terms (2^-11 of the magnitude) sit in their own columns, so their small addends
+//     are never truncated against the large main sums.
 constexpr int TC_CHUNK = 8;                     // k-blocks per main-accumulator chunk
-constexpr int TC_TMEM_COLS = 512;               // main0 | main1 | small0 | small1
+constexpr int TC_TMEM_COLS = 512;               // main0 | corr0 | main1 | corr1
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -133,7 +135,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // fastest) with the shared-memory ring, the main-accumulator ping-pong and a double-buffered
 // correction accumulator all running ACROSS tiles: the TMA producer and the MMA issuer start tile
 // t+1 while the epilogue warps still drain / store tile t, so neither the pipeline fill nor the
-// epilogue is exposed per tile.  TMEM (512 columns): main0 | main1 | small0 | small1.
+// epilogue is exposed per tile.  TMEM (512 columns): main0 | corr0 | main1 | corr1.
 template <int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -145,8 +147,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t mfull_bar[2];     // main accumulator chunk complete
   __shared__ __align__(8) uint64_t mempty_bar[2];    // main accumulator drained (4 epilogue warps)
-  __shared__ __align__(8) uint64_t sfull_bar[2];     // every MMA of a tile complete (its correction accumulator is final)
-  __shared__ __align__(8) uint64_t sempty_bar[2];    // correction accumulator drained (4 epilogue warps)
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,7 +183,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CX + CY - 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mfull_bar[b], 1); mbar_init(&mempty_bar[b], 4);
-      mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,7 +195,6 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   if (MC > 1) tc_cluster_sync();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
-  const uint32_t tmem_small = tmem_acc + 2 * TC_BN;
 
   if (warp == 0) {
     // ===================== TMA producer
@@ -235,13 +233,9 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN);
-      uint32_t it = 0, gc = 0, t = 0;                        // k-blocks, main chunks, tiles so far
-      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++t) {
-        const uint32_t sb = t & 1u;
-        mbar_wait(&sempty_bar[sb], ((t >> 1) & 1u) ^ 1u);    // correction accumulator sb drained (tile t - 2)
-        tc_fence_after();
-        const uint32_t tmem_sm = tmem_small + sb * TC_BN;
+      constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN), idesc2 = make_tf32_idesc(TC_BM, 2 * TC_BN);
+      uint32_t it = 0, gc = 0;                               // k-blocks, accumulator chunks so far
+      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = (int)(it % TC_STAGES);
           const uint32_t ph = (it / TC_STAGES) & 1u;
@@ -255,28 +249,28 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           tc_fence_after();
           const uint32_t base = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
           const uint64_t dAh = make_kmajor_sw128_desc(base + 0 * TC_TILE_BYTES), dAl = make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
-          const uint64_t dBh = make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES), dBl = make_kmajor_sw128_desc(base + 3 * TC_TILE_BYTES);
-          const uint32_t tmem_main = tmem_acc + buf * TC_BN;
+          const uint64_t dBh = make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES);   // Bh, and Bl right behind it
+          const uint32_t tmem_main = tmem_acc + buf * (2 * TC_BN);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // +32 bytes per K=8 step inside the 128-byte row
-            umma_tf32(tmem_main, dAh + adv, dBh + adv, idesc, !(first && k == 0));
-            umma_tf32(tmem_sm, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
-            umma_tf32(tmem_sm, dAl + adv, dBh + adv, idesc, 1u);
+            // Ah * [Bh ; Bl]^T in ONE N = 256 MMA: columns 0-127 main term, 128-255 first correction
+            // (Ah is read from shared memory once instead of twice)
+            umma_tf32(tmem_main, dAh + adv, dBh + adv, idesc2, !(first && k == 0));
+            umma_tf32(tmem_main + TC_BN, dAl + adv, dBh + adv, idesc, 1u);       // second correction, N = 128
           }
           if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
           else umma_commit_mc(&empty_bar[s], peers_mask);
           if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) { umma_commit(&mfull_bar[buf]); ++gc; }
         }
-        umma_commit(&sfull_bar[sb]);                         // every MMA of the tile complete
       }
     }
   } else {
     // ===================== epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t gc = 0, t = 0;
-    for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++t) {
+    uint32_t gc = 0;
+    for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
       int m0, n0;
       tile_of(ct, m0, n0);
       const int row = m0 + q * 32 + lane;
@@ -288,28 +282,22 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         mbar_wait(&mfull_bar[buf], (gc >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
+        for (int c = 0; c < TC_BN / 32; ++c) {               // main columns, then the chunk's correction columns
           uint32_t v[32];
-          tmem_ld32(tmem_acc + lane_off + (uint32_t)(buf * TC_BN + c * 32), v);
+          tmem_ld32(tmem_acc + lane_off + (uint32_t)(buf * 2 * TC_BN + TC_BN + c * 32), v);      // corrections first (small)
+          float corr[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) corr[j] = __uint_as_float(v[j]);
+          tmem_ld32(tmem_acc + lane_off + (uint32_t)(buf * 2 * TC_BN + c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]) + corr[j];
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&mempty_bar[buf]);
       }
-      const uint32_t sb = t & 1u;
-      mbar_wait(&sfull_bar[sb], (t >> 1) & 1u);
-      tc_fence_after();
 #pragma unroll
       for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_small + lane_off + (uint32_t)(sb * TC_BN + c * 32), v);
-        if (c == TC_BN / 32 - 1) {                           // correction accumulator fully read: hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sempty_bar[sb]);
-        }
         if (row < M) {
           const int nb = n0 + c * 32;
           float* crow = C + (int64_t)row * ldc + nb;
@@ -320,7 +308,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
             float o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float x = acc[c * 32 + j + u] + __uint_as_float(v[j + u]);
+              float x = acc[c * 32 + j + u];
               if (nb + j + u < N) {
                 if (flags & TC_BIAS) x += bias[nb + j + u];
                 if (flags & TC_RELU) x = fmaxf(x, 0.f);
