@@ -17,8 +17,8 @@
 // Structure (persistent: a CTA -- or a cluster of 2 / 4 -- walks 128x128 output tiles; 192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes of 128 rows x 32 floats)
 //               of Ah, Al, Bh, Bl into a 3-stage smem ring, mbarrier expect_tx
-//   warp 1      MMA issuer: one elected lane issues 4 k-steps x 3 terms of
-//               tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) per stage, accumulators
+//   warp 1      MMA issuer: one elected lane issues, per stage, 4 k-steps x 2 instructions of
+//               tcgen05.mma.cta_group::1.kind::tf32 (M128 N256 K8 and M128 N128 K8), accumulators
 //               in tensor memory; tcgen05.commit releases the smem stage / signals the epilogue
 //   warps 2-5   drain + epilogue: tcgen05.ld 32x32b (each warp its own TMEM lane quarter),
 //               two-level accumulation (see below), fused bias / relu / relu-mask, float4 stores
