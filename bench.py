@@ -4,23 +4,31 @@
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
 prints ONE JSON line on rank 0.  A "step" is one train step (one hot-loop iteration,
 model.py:221-222: dataset batch + key splits + eps draw + forward + ELBO + backward + Adam)
-of EVERY packed model; K steps run in one persistent launch.
+of EVERY packed model; K steps are ONE persistent launch (`vae_pack_train`).
 
-Workload (config.workload): BASELINE.json configs[1] -- the sigmoid padding VAE
+Headline workload (config.workload): BASELINE.json configs[1] -- the sigmoid padding VAE
 `sigmoid_vae_padding_expts.sh:1` (dd=3, pd=3 -> D=7, L=6, two decoders, B=100, lr 1e-4,
-eps0=-3, -tdv) -- packed as M independent runs per GPU that differ only in the dataset
-seed (the sweep's seed axis).  M models are sharded per rank with no communication
-("scaling": "weak").  `--workload` selects other single-Dense shapes of the sweeps;
-`--models 1` gives the literal single-model chain.
+eps0=-3, -tdv) -- packed as 1184 independent runs per GPU that differ only in the dataset
+seed (the sweep's seed axis), sharded per rank with no communication ("scaling": "weak").
+
+Timing: after W warm-up steps the K-step launch is repeated R times back to back (R chosen so
+the timed window is >= 50 ms), a CUDA event between launches; `ms_per_step` = median launch
+duration / K, max over ranks; the window is bracketed by barrier + synchronize.
+
+`sub_results` carries the other BASELINE.json configs measured the same way in the same run,
+each with its own roofline: the literal single chain, the sphere pack (configs[2]), the single
+sphere chain, the 54-run sweep mix for K steps (configs[3]) and the data-parallel cfg5 step
+(configs[4], NCCL gradient allreduce when WORLD_SIZE > 1).
 
 --impl reference: the CPU oracle port (oracle/c, all host threads) on a bounded sample of
 the same workload.  The real reference (JAX/Flax) cannot be installed here: no jax/flax
-wheels, no network.
+wheels, no network; the line says which CPU arm ran.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,6 +42,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "vae_train_steps_per_sec_summed_over_packed_models"
 UNIT = "train-steps/s"
+HEADLINE_MODELS = 1184          # 148 SMs x 8 resident models per SM of the configs[1] kernel
+MIN_WINDOW_MS = 50.0
 
 WORKLOADS = {
     # name: (dataset, dd, pd, L, lr, eps0, first dataset seed, reference line, hidden)
@@ -43,8 +53,6 @@ WORKLOADS = {
     "sphere_dd3_pd3_ld6": ("sphere", 3, 3, 6, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:1", (200, 200, 200)),
     "sphere_dd5_pd16_ld16": ("sphere", 5, 16, 16, 1e-4, -3.0, 69, "sphere_vae_padding_expts.sh:3", (200, 200, 200)),
 }
-# dram bytes (read + write) of one captured launch of the workload's fused kernel, from profiles/ (ncu --set full)
-NCU_TRAFFIC = {"sigmoid_dd3_pd3_ld6": 2779904 + 68352}
 # BASELINE.json configs[4]: ONE scaled sphere VAE, data-parallel with an NCCL gradient allreduce
 # (D = 512 + 512, width 4096 x 3, batch 65 536, L = 16 -- L is our choice)
 DP_WORKLOADS = {
@@ -56,12 +64,15 @@ DP_WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100000)
-    ap.add_argument("--warmup", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sigmoid_dd3_pd3_ld6", choices=sorted(WORKLOADS) + sorted(DP_WORKLOADS))
-    ap.add_argument("--models", type=int, default=0, help="models packed per GPU (0 = 148 SMs x resident CTAs)")
+    ap.add_argument("--models", type=int, default=0, help="models packed per GPU (0 = the GPU-filling default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub_results (other BASELINE configs)")
+    ap.add_argument("--no-ab", action="store_true", help="skip the eps-sharing A/B launches")
+    ap.add_argument("--dp-steps", type=int, default=3, help="timed steps of the cfg5 data-parallel sub-result")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -79,6 +90,36 @@ def make_specs(workload, n_models, first_index=0):
                     name=f"{workload}_ds{seed0 + first_index + i}") for i in range(n_models)]
 
 
+def workload_config(workload, n_models):
+    """The `config` both arms print for a packed workload (the reference arm samples it)."""
+    wl = WORKLOADS[workload]
+    D = wl[1] + wl[2] + (1 if wl[0] == "sigmoid" else 0)
+    return {"workload": f"{workload} ({wl[7]}; BASELINE.json {'configs[2]' if wl[8] else 'configs[1]'} shape) x "
+                        f"{n_models} independent dataset seeds packed per GPU",
+            "batch": 100, "models_per_gpu": n_models, "data_dim": D, "latent_dim": wl[3]}
+
+
+def reference_probe():
+    """probe for a usable reference runtime at the start of every run."""
+    def has(mod):
+        try:
+            __import__(mod)
+            return True
+        except Exception:
+            return False
+    return {"jax": has("jax"), "flax": has("flax"), "baseline_ref": os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))}
+
+
+def traffic_of(key):
+    """dram bytes (read + write) per launch of the named capture, from profiles/traffic.json
+    (written from `ncu --set full` captures of exactly that command); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 # ------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -92,10 +133,11 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.25)         # let nvidia-smi start sampling before the timed window opens
         except OSError:
             self.proc = None
 
@@ -106,7 +148,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -131,8 +173,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------- CPU arms
-def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50):
-    """Times the C oracle port (oracle/c) on n_models independent runs; returns steps/s."""
+def cpu_oracle_jobs(workload, n_models, max_steps):
     from oracle import c_oracle as co
     from oracle import datasets as ods
     from oracle import jax_random as jr
@@ -147,95 +188,140 @@ def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50):
         _, key = jr.model_chain_next(key)
         _, key = jr.model_chain_next(key)
         ds.get_key()
-        jobs.append(co.Job(co.make_desc(d), co.make_data(name, dd, pd), flat, key, ds.key, ds.A, n_steps))
-    co.train_loop(jobs, warm_steps, n_threads)
-    t0 = time.perf_counter()
-    co.train_loop(jobs, n_steps, n_threads)
-    dt = time.perf_counter() - t0
+        jobs.append(co.Job(co.make_desc(d), co.make_data(name, dd, pd), flat, key, ds.key, ds.A, max_steps))
+    return jobs
+
+
+def cpu_oracle_run(workload, n_models, n_steps, n_threads, warm_steps=50, repeats=1):
+    """Times the C oracle port (oracle/c): `repeats` back-to-back passes of n_steps steps of n_models
+    independent runs.  Returns (steps/s from the median pass, median pass seconds, total seconds)."""
+    from oracle import c_oracle as co
+    jobs = cpu_oracle_jobs(workload, n_models, max(n_steps, warm_steps))
+    if warm_steps > 0:
+        co.train_loop(jobs, warm_steps, n_threads)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        co.train_loop(jobs, n_steps, n_threads)
+        times.append(time.perf_counter() - t0)
     assert all(np.isfinite(j.loss[:n_steps]).all() for j in jobs)
-    return n_models * n_steps / dt, dt
+    med = float(np.median(times))
+    return n_models * n_steps / med, med, float(np.sum(times))
 
 
 def cpu_baseline(workload, target_seconds):
     cores = os.cpu_count() or 1
     n_models = cores
-    rate, _ = cpu_oracle_run(workload, n_models, 40, cores, warm_steps=5)         # calibrate
+    rate, _, _ = cpu_oracle_run(workload, n_models, 40, cores, warm_steps=5)         # calibrate
     n_steps = max(20, int(rate * target_seconds / n_models))
-    rate, dt = cpu_oracle_run(workload, n_models, n_steps, cores)
+    rate, dt, _ = cpu_oracle_run(workload, n_models, n_steps, cores)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n_models} independent {workload} runs x {n_steps} steps, oracle/c (plain C, float32, "
                       f"AVX2) on {cores} threads, {dt:.1f} s; restated CPU oracle -- NOT the reference JAX runtime"}
 
 
 def run_reference(args):
+    """The reference arm: the path's CPU implementation on the host cores.  The JAX/Flax runtime is not
+    installable (reference_probe), so this is the oracle port; each `step` trains one model per host
+    thread (a bounded sample of the arm's pack) and the K-step pass is repeated for >= 2.5 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n_models = cores
-    rate, _ = cpu_oracle_run(args.workload, n_models, 40, cores, warm_steps=5)
-    # each "step" of this arm = one train step of each of n_models models; bound the run to ~minutes
-    k = max(1, min(args.steps, int(rate * 20.0 / n_models)))
-    w = max(3, min(args.warmup, max(3, k // 10)))
-    rate, dt = cpu_oracle_run(args.workload, n_models, k, cores, warm_steps=w)
-    wl = WORKLOADS[args.workload]
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
-            "warmup": w, "ms_per_step": dt / k * 1e3, "higher_is_better": True, "scaling": "weak",
+    workload = args.workload if args.workload in WORKLOADS else "sigmoid_dd3_pd3_ld6"
+    K = max(1, int(args.steps))
+    W = max(3, int(args.warmup))
+    rate, _, _ = cpu_oracle_run(workload, n_models, 40, cores, warm_steps=5)         # calibrate
+    K_run = max(1, min(K, int(rate * 60.0 / n_models)))                              # one pass <= ~60 s
+    t_pass = K_run * n_models / rate
+    R = int(min(100000, max(3, math.ceil(2.5 / t_pass))))
+    rate, med, total = cpu_oracle_run(workload, n_models, K_run, cores, warm_steps=min(W, 200), repeats=R)
+    pack = args.models if args.models > 0 else (HEADLINE_MODELS if not wl_hidden(workload) else 148)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K_run,
+            "warmup": W, "ms_per_step": med / K_run * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} ({wl[7]}) x {n_models} independent runs on host cores",
-                       "batch": 100, "models": n_models},
+            "config": workload_config(workload, pack),
+            "timing": {"repeats": R, "window_ms": total * 1e3, "per_launch": "median of the repeats"},
+            "reference_probe": reference_probe(),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n_models} runs x {k} steps on {cores} threads (oracle/c); the reference's "
+                             "sample": f"{n_models} of the pack's runs (one per host thread) x {K_run} steps x {R} "
+                                       f"repeats on {cores} threads, {total:.1f} s (oracle/c); the reference's "
                                        "JAX/Flax runtime is not installable here (no wheels, no network)"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------- GPU arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from vae_training_b200 import init, ops
-    from vae_training_b200.packed import PackedRuns
+# ---------------------------------------------------------------------- GPU arm helpers
+class Ctx:
+    """torch / distributed context of one rank."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    K, W = int(args.steps), max(3, int(args.warmup))
-    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    if args.models > 0:
-        n_models = args.models
-    else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
-        probe = PackedRuns(make_specs(args.workload, 1), max_chunk=4)
-        n_models = max(1, ops.fused_resident_jobs(probe.jobs[0]))
-        if n_models >= 8 and not wl_hidden(args.workload):
-            n_models -= n_models % 8      # whole CTAs of 4 models / whole cluster pairs (fused_small.cu)
-        del probe
-    specs = make_specs(args.workload, n_models, first_index=rank * n_models)
-    runs = PackedRuns(specs, max_chunk=max(K, W))
-    states = [init.initial_state(s) for s in specs]
-    runs.upload(states)
-    torch.cuda.synchronize()
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t)
 
-    # FFMA peak probe (roofline denominator for this on-chip, non-HBM, non-tensor kernel)
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed_repeats(ctx, launch, est_ms=None, min_window_ms=MIN_WINDOW_MS, max_repeats=4000):
+    """Repeats `launch()` (which enqueues one K-step unit of work on the current stream) back to back
+    until the window is >= min_window_ms; CUDA events between launches.  Returns (median ms per launch
+    (max over ranks), window ms (max over ranks), repeats)."""
+    torch = ctx.torch
+    if est_ms is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        torch.cuda.synchronize()
+        est_ms = max(e0.elapsed_time(e1), 1e-3)
+    R = int(min(max_repeats, max(3, math.ceil(min_window_ms / est_ms))))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    ctx.barrier()
+    ev[0].record()
+    for i in range(R):
+        launch()
+        ev[i + 1].record()
+    ctx.barrier()
+    d = [ev[i].elapsed_time(ev[i + 1]) for i in range(R)]
+    return ctx.max_over_ranks(float(np.median(d))), ctx.max_over_ranks(ev[0].elapsed_time(ev[R])), R
+
+
+def ffma_peak(ctx):
+    """FP32 FFMA throughput measured in this run: the roofline denominator of the on-chip FFMA kernels."""
+    from vae_training_b200 import ops
+    torch = ctx.torch
     sink = torch.zeros(148 * 8 * 256, device="cuda")
     ops.ffma_probe(148 * 8, 256, 2000, sink)
     torch.cuda.synchronize()
@@ -244,151 +330,16 @@ def run_b200(args):
     flops = ops.ffma_probe(148 * 8, 256, 20000, sink)
     e1.record()
     torch.cuda.synchronize()
-    ffma_tflops = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
-
-    # ---- device-resident arm
-    runs.upload(states)
-    runs.train_steps(W)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from vae_training_b200 import _lib
-    l0 = _lib.load().vae_launch_count()
-    e0.record()
-    runs.train_steps(K)
-    e1.record()
-    launches = _lib.load().vae_launch_count() - l0
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop() if rank == 0 else None
-    loss_dev = runs.loss.view(n_models, runs.max_chunk)[:, :K]
-    if not bool(torch.isfinite(loss_dev).all()):
-        raise SystemExit("bench.py: non-finite loss in the timed region")
-    loss_snapshot = loss_dev.clone()
-    total_models = n_models * world
-    value = total_models * K / (ms * 1e-3)
-
-    # ---- A/B: the same pack and steps with eps sharing off / through 2-CTA clusters instead
-    ab = {}
-    if not wl_hidden(args.workload):
-        for mode, env in (("private_eps_draw", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "1"}),
-                          ("cluster2_dsmem", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "2"})):
-            os.environ.update(env)
-            runs.upload(states)
-            runs.train_steps(W)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            runs.train_steps(K)
-            e1.record()
-            barrier()
-            ab[mode] = total_models * K / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
-            for k in env:
-                del os.environ[k]
-            if not torch.equal(loss_snapshot, runs.loss.view(n_models, runs.max_chunk)[:, :K]):
-                raise SystemExit(f"bench.py: {mode} and the default launch disagree (must be bit-identical)")
-
-    # ---- end-to-end arm: host state in (pinned), fused steps, losses + state out
-    runs.train_host(states, W)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    h2d = runs.upload(states)
-    runs.train_steps(K)
-    d2h = runs.download(K)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = total_models * K / (ms_e2e * 1e-3)
-    hl = runs.hloss[:n_models * K].numpy()
-    if not np.isfinite(hl).all():
-        raise SystemExit("bench.py: non-finite loss in the end-to-end region")
-
-    if rank == 0:
-        spec = specs[0]
-        wl = WORKLOADS[args.workload]
-        flop_step = spec.flops_per_step()
-        achieved = flop_step * (n_models * K) / (ms * 1e-3) / 1e12         # per GPU, algorithmic flops only
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "samples_per_sec": value * spec.batch_size,
-            "config": {"workload": f"{args.workload} ({wl[7]}; BASELINE.json {'configs[2]' if wl[8] else 'configs[1]'} shape) x {n_models} "
-                                   f"independent dataset seeds packed per GPU", "batch": spec.batch_size,
-                       "models_per_gpu": n_models, "data_dim": spec.data_dim, "latent_dim": spec.latent_dimension,
-                       "l2_flush": "n/a: working set is SM-resident (shared memory); HBM traffic is the 4-byte "
-                                   "loss store per model-step",
-                       "eps_draw": "4 models per CTA (512 threads); the models of a CTA whose carried model key is "
-                                   "equal (always, here: the reference seeds every model with PRNGKey(0), model.py:29) "
-                                   "share one threefry/normal draw of eps per step -- bit-identical to private draws "
-                                   "(checked in this run against both A/B launches, see eps_sharing_ab)",
-                       "parallelism": f"independent models x{world} GPUs, no collective"},
-            "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-                    "note": "PackedRuns.train_host: pinned host state -> device, K fused steps, per-step losses + "
-                            "final state -> host"},
-            "eps_sharing_ab": {"unit": UNIT, **ab,
-                               "note": "same pack and steps; private_eps_draw: one model per CTA, every model draws its "
-                                       "own eps; cluster2_dsmem: one model per CTA, pairs share the draw through DSMEM"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
-                         "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
-                         "traffic": NCU_TRAFFIC.get(args.workload),
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE 2000-step launch of this "
-                                         "kernel (ncu --set full, profiles/r01_fused_small_v4_ncu_full.txt): the job "
-                                         "table + initial state; per-step losses are absorbed by L2 within a launch",
-                         "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one "
-                                 f"GPU; peak = FFMA probe measured in this run ({ffma_tflops:.1f} TFLOP/s); RNG work "
-                                 f"({spec.normals_per_step()} threefry normals/model-step) is not counted as flops",
-                         "normals_per_sec_per_gpu": spec.normals_per_step() * n_models * K / (ms * 1e-3)},
-        }
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
-def run_dp(args):
-    """One large model, data-parallel over the ranks (strong scaling: the global batch is fixed)."""
-    import torch
-    import torch.distributed as dist
-    from vae_training_b200 import dp, init, ops
-    from vae_training_b200.packed import RunSpec
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = DP_WORKLOADS[args.workload]
-    K = int(args.steps) if args.steps != 100000 else 6
-    W = max(3, int(args.warmup) if args.warmup != 2000 else 3)
-    spec = RunSpec("sphere", w["dd"], w["pd"], w["L"], w["hidden"], w["hidden"], batch_size=w["batch"],
-                   learning_rate=w["lr"], epsilon=w["eps0"], tunable_decoder_var=True, dataset_seed=w["seed"])
-    st = init.initial_state(spec)
-    model = dp.DataParallelVAE(spec, st.params, st.model_key, st.dataset_key, st.A)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-
-    # TF32 tensor peak measured in this run (cuBLAS, 8192^3) -- the denominator for a 3xTF32 kernel
+def tf32_peak(ctx):
+    """cuBLAS TF32 GEMM throughput measured in this run (8192^3): denominator of the tensor-core kernels
+    (MEASURED_PEAKS.json holds only bf16: 1664.7 burst / 1383.5 sustained TFLOP/s)."""
+    torch = ctx.torch
     a = torch.randn(8192, 8192, device="cuda")
     b = torch.randn(8192, 8192, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     for _ in range(3):
         torch.matmul(a, b)
@@ -399,37 +350,149 @@ def run_dp(args):
         torch.matmul(a, b)
     e1.record()
     torch.cuda.synchronize()
-    tf32_peak = 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    torch.backends.cuda.matmul.allow_tf32 = False
-    del a, b
+    torch.backends.cuda.matmul.allow_tf32 = old
+    return 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
+
+def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key):
+    flop_step = spec.flops_per_step()
+    achieved = flop_step * n_models * K / (ms_launch * 1e-3) / 1e12            # per GPU, algorithmic flops only
+    return {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic_of(traffic_key),
+            "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                            f"'{traffic_key}' in profiles/traffic.json (null = not captured for this exact command)",
+            "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one GPU over the "
+                    f"median launch; peak = FFMA probe measured in this run ({peak:.1f} TFLOP/s); RNG work "
+                    f"({spec.normals_per_step()} threefry normals/model-step) is not counted as flops",
+            "normals_per_sec_per_gpu": spec.normals_per_step() * n_models * K / (ms_launch * 1e-3)}
+
+
+def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states=False):
+    """Device-resident throughput of one homogeneous pack: W warm-up steps, then R x (K-step launch)."""
+    from vae_training_b200 import _lib, init
+    from vae_training_b200.packed import PackedRuns
+    torch = ctx.torch
+    specs = make_specs(workload, n_models, first_index=first_index)
+    runs = PackedRuns(specs, max_chunk=max(K, W))
+    states = [init.initial_state(s) for s in specs]
+    runs.upload(states)
+    runs.prepare()
+    runs.train_steps(W)
+    torch.cuda.synchronize()
+    l0 = _lib.load().vae_launch_count()
+    ms, window, R = timed_repeats(ctx, lambda: runs.train_steps(K))
+    launches = _lib.load().vae_launch_count() - l0
+    loss_dev = runs.loss.view(n_models, runs.max_chunk)[:, :K]
+    if not bool(torch.isfinite(loss_dev).all()):
+        raise SystemExit(f"bench.py: non-finite loss in the timed region ({workload})")
+    total = n_models * ctx.world
+    out = {"value": total * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
+           "models_per_gpu": n_models, "samples_per_sec": total * K / (ms * 1e-3) * specs[0].batch_size,
+           "timing": {"repeats": R, "window_ms": window, "launch_ms_median": ms},
+           "launch_plan": {"class": runs.plan.cls, "models_per_cta": runs.plan.gm, "cluster": runs.plan.cluster},
+           "gpu_launches": int(launches),
+           "roofline": pack_roofline(specs[0], n_models, K, ms, peak, f"{workload}_m{n_models}_k{K}")}
+    if want_states:
+        return out, runs, specs, states
+    del runs
+    return out
+
+
+def measure_sweep_mix(ctx, K, W, peak):
+    """BASELINE.json configs[3] for K steps: the 54 runs of the three scripts (LPT-partitioned over the
+    ranks, no communication), single-Dense runs and hidden-layer runs as two concurrent packs."""
+    from vae_training_b200 import init, sweep
+    from vae_training_b200.packed import PackedRuns, RunSpec
+    from vae_training_b200.vae import _parse_sizes
+    torch = ctx.torch
+    all_args = sweep.builtin_runs("all")
+    mine = sweep.lpt_partition([sweep.run_cost(a) for a in all_args], ctx.world)[ctx.rank]
+    specs = [RunSpec(dataset=a.dataset, dataset_dimension=a.dataset_dimension, padding_dim=a.padding_dim,
+                     latent_dimension=a.latent_dimension, layer_sizes=_parse_sizes(a.layer_sizes),
+                     encoder_layer_sizes=_parse_sizes(a.encoder_layer_sizes), batch_size=a.batch_size,
+                     learning_rate=a.learning_rate, epsilon=a.epsilon, tunable_decoder_var=a.tunable_decoder_var,
+                     dataset_seed=a.dataset_seed, dataset_intrinsic_dimension=a.dataset_intrinsic_dimension,
+                     num_batches=a.num_batches, name=a.name) for a in (all_args[i] for i in mine)]
+    groups = [[s for s in specs if not s.layer_sizes], [s for s in specs if s.layer_sizes]]
+    packs, streams = [], []
+    for g in groups:
+        if not g:
+            continue
+        r = PackedRuns(g, max_chunk=max(K, W))
+        r.upload([init.initial_state(s) for s in g])
+        r.prepare()
+        packs.append(r)
+        streams.append(torch.cuda.Stream())
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream()
+
+    def launch(n):
+        start = torch.cuda.Event()
+        start.record(main)
+        for r, st in zip(packs, streams):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                r.train_steps(n)
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+    launch(W)
+    torch.cuda.synchronize()
+    # a rank without runs (more ranks than runs) still takes part in the barriers / reductions
+    ms, window, R = timed_repeats(ctx, lambda: launch(K), est_ms=None if packs else MIN_WINDOW_MS)
+    for r in packs:
+        if not bool(torch.isfinite(r.loss.view(r.M, r.max_chunk)[:, :K]).all()):
+            raise SystemExit("bench.py: non-finite loss in the sweep mix")
+    flops = ctx.sum_over_ranks(float(sum(s.flops_per_step() for s in specs)))     # one step of every run, all ranks
+    achieved = flops * K / (ms * 1e-3) / 1e12 / ctx.world
+    return {"value": len(all_args) * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
+            "runs": len(all_args), "runs_this_rank": len(specs),
+            "timing": {"repeats": R, "window_ms": window, "launch_ms_median": ms},
+            "roofline": {"bound": "fp32-alu / latency (15 hidden-layer chains set the time; SURVEY.md 0.5)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "note": "achieved = algorithmic flops of one step of all 54 runs x K / median launch, per GPU"},
+            "config": {"workload": "all 54 runs of seed_linpadding_expts.sh, sigmoid_vae_padding_expts.sh, "
+                                   "sphere_vae_padding_expts.sh advanced K steps together (BASELINE.json configs[3]); "
+                                   "one single-Dense pack + one hidden-layer pack on two streams per GPU",
+                       "parallelism": f"LPT partition over {ctx.world} GPU(s), no collective"}}
+
+
+def measure_dp(ctx, workload, K, W):
+    """BASELINE.json configs[4]: one large model, data-parallel over the ranks (strong scaling: the global
+    batch is fixed); NCCL sum-allreduce of the gradient when WORLD_SIZE > 1."""
+    from vae_training_b200 import _lib, dp, init
+    from vae_training_b200.packed import RunSpec
+    torch = ctx.torch
+    world = ctx.world
+    w = DP_WORKLOADS[workload]
+    spec = RunSpec("sphere", w["dd"], w["pd"], w["L"], w["hidden"], w["hidden"], batch_size=w["batch"],
+                   learning_rate=w["lr"], epsilon=w["eps0"], tunable_decoder_var=True, dataset_seed=w["seed"])
+    peak = tf32_peak(ctx)
+    st = init.initial_state(spec)
+    model = dp.DataParallelVAE(spec, st.params, st.model_key, st.dataset_key, st.A)
     for _ in range(W):
         model.train_step()
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    ctx.barrier()
     losses = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from vae_training_b200 import _lib
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     l0 = _lib.load().vae_launch_count()
-    e0.record()
-    for _ in range(K):
+    ev[0].record()
+    for i in range(K):
         losses.append(model.train_step().clone())
-    e1.record()
+        ev[i + 1].record()
     launches = _lib.load().vae_launch_count() - l0
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop() if rank == 0 else None
+    ctx.barrier()
+    ms = ctx.max_over_ranks(ev[0].elapsed_time(ev[K])) / K
     lv = torch.cat(losses).cpu().numpy()
     if not np.isfinite(lv).all():
-        raise SystemExit("bench.py: non-finite loss in the timed region")
+        raise SystemExit("bench.py: non-finite loss in the data-parallel timed region")
     # end to end through the host-facing call: carried keys in from pinned host memory, loss out
     hkeys = torch.zeros(4, dtype=torch.uint32).pin_memory()
     hloss = torch.zeros(1, dtype=torch.float32).pin_memory()
     hkeys[:2].copy_(model.key.cpu())
     hkeys[2:].copy_(model.dkey.cpu())
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
@@ -441,39 +504,189 @@ def run_dp(args):
         hkeys[2:].copy_(model.dkey, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ctx.barrier()
+    ms_e2e = ctx.max_over_ranks(e0.elapsed_time(e1)) / K
+    flop_step = spec.flops_per_step()
+    value = 1.0 / (ms * 1e-3)
+    achieved = flop_step * value / world / 1e12
+    out = {"value": value, "unit": UNIT, "ms_per_step": ms, "steps": K, "warmup": W, "scaling": "strong",
+           "samples_per_sec": value * spec.batch_size, "losses": [float(v) for v in lv],
+           "dtype": "f32 (3xTF32 tensor-core GEMMs, FP32 accumulate)",
+           "config": {"workload": f"{workload}: one sphere VAE D={spec.data_dim} L={spec.latent_dimension} hidden="
+                                  f"{list(w['hidden'])} global batch {spec.batch_size} (BASELINE.json configs[4])",
+                      "batch": spec.batch_size, "rows_per_gpu": model.rows, "params": model.n,
+                      "l2_flush": "inputs larger than L2 (activations >= 1 GB per layer)",
+                      "parallelism": f"dp{world}: row-pair sharded batch, " +
+                                     (f"NCCL sum-allreduce of {(model.n + 1) * 4 / 1e6:.1f} MB per step, " if world > 1
+                                      else "no collective at one GPU, ") + "replicated Adam"},
+           "e2e": {"value": 1.0 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 20,
+                   "note": "inputs of a step are the two carried PRNG keys (batch and eps are generated on the device, "
+                           "as in the reference); loss and keys are read back every step"},
+           "gpu_launches": int(launches),
+           "gpu_launches_note": "kernels of libvae_b200.so launched in the timed region (vae_launch_count); torch copy "
+                                "/ NCCL kernels are not counted",
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "note": f"achieved = {flop_step / 1e12:.2f} algorithmic TFLOP/step / {world} GPUs / step time; "
+                                f"peak = cuBLAS TF32 GEMM measured in this run ({peak:.0f} TFLOP/s; MEASURED_PEAKS.json "
+                                "holds only bf16: 1664.7 burst / 1383.5 sustained).  FP32-level accuracy costs three "
+                                "TF32 MMAs per product, so frac <= 1/3 by construction"}}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    from vae_training_b200 import ops
+    from vae_training_b200.packed import PackedRuns
+    world, rank = ctx.world, ctx.rank
+    K, W = int(args.steps), max(3, int(args.warmup))
+    workload = args.workload
+    if args.models > 0:
+        n_models = args.models
+    elif workload == "sigmoid_dd3_pd3_ld6":
+        n_models = HEADLINE_MODELS
+    else:      # fill the GPU: resident CTAs per SM of this shape's kernel x SM count
+        probe = PackedRuns(make_specs(workload, 1), max_chunk=4)
+        n_models = max(1, ops.fused_resident_jobs(probe.jobs[0]))
+        if n_models >= 8 and not wl_hidden(workload):
+            n_models -= n_models % 8      # whole CTAs of 4 models / whole cluster pairs (fused_small.cu)
+        del probe
+    peak = ffma_peak(ctx)
+
+    # ---- headline: device-resident arm
+    clocks = ClockSampler(ctx.local)
     if rank == 0:
-        flop_step = spec.flops_per_step()
-        value = K / (ms * 1e-3)
-        achieved = flop_step * value / world / 1e12
+        clocks.start()
+    head, runs, specs, states = measure_pack(ctx, workload, n_models, K, W, peak, first_index=rank * n_models,
+                                             want_states=True)
+    clk = clocks.stop() if rank == 0 else None
+    resident = ops.fused_resident_jobs(runs.jobs[0])
+    loss_snapshot = runs.loss.view(n_models, runs.max_chunk)[:, :K].clone()
+    total_models = n_models * world
+
+    # ---- A/B: the same pack and steps with eps sharing off / through 2-CTA clusters instead
+    ab = {}
+    if not wl_hidden(workload) and not args.no_ab:
+        runs.upload(states)
+        runs.prepare()
+        runs.train_steps(W)
+        runs.train_steps(K)
+        torch.cuda.synchronize()
+        loss_snapshot = runs.loss.view(n_models, runs.max_chunk)[:, :K].clone()     # steps W .. W+K from the initial state
+        for mode, env in (("private_eps_draw", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "1"}),
+                          ("cluster2_dsmem", {"VAE_SMALL_GM": "1", "VAE_SMALL_CLUSTER": "2"})):
+            os.environ.update(env)
+            runs.upload(states)
+            runs.prepare()                  # the launch-shaping knobs are read when the pack is prepared
+            runs.train_steps(W)
+            runs.train_steps(K)
+            torch.cuda.synchronize()
+            if not torch.equal(loss_snapshot, runs.loss.view(n_models, runs.max_chunk)[:, :K]):
+                raise SystemExit(f"bench.py: {mode} and the default launch disagree (must be bit-identical)")
+            ms_ab, _, _ = timed_repeats(ctx, lambda: runs.train_steps(K))
+            ab[mode] = total_models * K / (ms_ab * 1e-3)
+            for k in env:
+                del os.environ[k]
+        runs.prepare()
+
+    # ---- end-to-end arm: pinned host state -> device, K fused steps, state + per-step losses -> host
+    runs.stage(states)                      # host-side packing into the pinned arena (not timed)
+
+    def e2e_unit():
+        h2d = runs.upload()
+        runs.train_steps(K)
+        d2h = runs.download(K)
+        return h2d, d2h
+    h2d, d2h = e2e_unit()
+    torch.cuda.synchronize()
+    ms_e2e, window_e2e, R_e2e = timed_repeats(ctx, e2e_unit)
+    e2e_value = total_models * K / (ms_e2e * 1e-3)
+    hl = runs.hloss[:n_models * K].numpy()
+    if not np.isfinite(hl).all():
+        raise SystemExit("bench.py: non-finite loss in the end-to-end region")
+    del runs
+
+    # ---- the other BASELINE.json configs, same run, same timing method
+    sub = {}
+    if not args.no_sub:
+        sub["single_chain"] = measure_pack(ctx, workload, 1, K, W, peak)
+        sub["single_chain"]["config"] = {"workload": f"{workload}: ONE model (the literal single chain of "
+                                                     f"{WORKLOADS[workload][7]}) per GPU"}
+        sph = "sphere_dd3_pd3_ld6"
+        probe = PackedRuns(make_specs(sph, 1), max_chunk=4)
+        n_sph = max(1, ops.fused_resident_jobs(probe.jobs[0]))
+        del probe
+        sub["sphere_pack"] = measure_pack(ctx, sph, n_sph, K, W, peak, first_index=rank * n_sph)
+        sub["sphere_pack"]["config"] = workload_config(sph, n_sph)
+        sub["sphere_single_chain"] = measure_pack(ctx, sph, 1, K, W, peak)
+        sub["sphere_single_chain"]["config"] = {"workload": f"{sph}: ONE hidden-layer model per GPU (the latency "
+                                                            "configuration: the long pole of the 8-GPU sweep)"}
+        sub["sweep_mix_54_runs"] = measure_sweep_mix(ctx, K, W, peak)
+        torch.cuda.empty_cache()
+        sub["cfg5_sphere_dp"] = measure_dp(ctx, "cfg5_sphere_dp", max(1, args.dp_steps), 3)
+
+    if rank == 0:
+        cfg = workload_config(workload, n_models)
+        cfg.update({
+            "resident_models_per_gpu": resident,
+            "l2_flush": "n/a: working set is SM-resident (shared memory); HBM traffic is the 4-byte "
+                        "loss store per model-step",
+            "eps_draw": "4 models per CTA (512 threads); the models of a CTA whose carried model key is "
+                        "equal (always, here: the reference seeds every model with PRNGKey(0), model.py:29) "
+                        "share one threefry/normal draw of eps per step -- bit-identical to private draws "
+                        "(checked in this run against both A/B launches, see eps_sharing_ab)",
+            "parallelism": f"independent models x{world} GPUs, no collective"})
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (3xTF32 tensor-core GEMMs, FP32 accumulate)", "data": "synthetic",
-            "samples_per_sec": value * spec.batch_size,
-            "config": {"workload": f"{args.workload}: one sphere VAE D={spec.data_dim} L={spec.latent_dimension} hidden="
-                                   f"{list(w['hidden'])} global batch {spec.batch_size} (BASELINE.json configs[4])",
-                       "batch": spec.batch_size, "rows_per_gpu": model.rows, "params": model.n,
-                       "l2_flush": "inputs larger than L2 (activations >= 1 GB per layer)",
-                       "parallelism": f"dp{world}: row-pair sharded batch, NCCL sum-allreduce of "
-                                      f"{(model.n + 1) * 4 / 1e6:.1f} MB per step, replicated Adam"},
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "samples_per_sec": head["samples_per_sec"],
+            "config": cfg,
+            "timing": dict(head["timing"], method="R back-to-back K-step launches (one vae_pack_train each), CUDA "
+                                                  "events between launches on the launching stream, median launch, "
+                                                  "max over ranks; barrier + synchronize around the window"),
+            "launch_plan": head["launch_plan"],
             "clocks": clk,
-            "e2e": {"value": K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 20,
-                    "note": "inputs of a step are the two carried PRNG keys (batch and eps are generated on the device, "
-                            "as in the reference); loss and keys are read back every step"},
-            "gpu_launches": int(launches),
-            "gpu_launches_note": "kernels of libvae_b200.so launched in the timed region (vae_launch_count); torch copy / NCCL kernels are not counted",
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": None,
-                         "note": f"achieved = {flop_step / 1e12:.2f} algorithmic TFLOP/step / {world} GPUs / step time; "
-                                 f"peak = cuBLAS TF32 GEMM measured in this run ({tf32_peak:.0f} TFLOP/s; MEASURED_PEAKS.json "
-                                 "holds only bf16: 1664.7 burst / 1383.5 sustained).  FP32-level accuracy costs three "
-                                 "TF32 MMAs per product, so frac <= 1/3 by construction"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                    "timing": {"repeats": R_e2e, "window_ms": window_e2e, "launch_ms_median": ms_e2e},
+                    "note": "per repeat: ONE H2D copy of the pinned state arena, K fused steps (vae_pack_train), "
+                            "ONE D2H copy of state + per-step losses (PackedRuns.upload / train_steps / download)"},
+            "eps_sharing_ab": {"unit": UNIT, **ab,
+                               "note": "same pack and steps; private_eps_draw: one model per CTA, every model draws its "
+                                       "own eps; cluster2_dsmem: one model per CTA, pairs share the draw through DSMEM"},
+            "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"],
+            "reference_probe": reference_probe(),
+            "sub_results": sub,
         }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(workload, args.cpu_seconds)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
+
+
+def run_dp(args):
+    """`--workload cfg5_*_dp`: the data-parallel configuration as the headline line."""
+    ctx = Ctx()
+    K = int(args.steps) if args.steps != 2000 else 6
+    W = max(3, int(args.warmup) if args.warmup != 200 else 3)
+    clocks = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        clocks.start()
+    r = measure_dp(ctx, args.workload, K, W)
+    clk = clocks.stop() if ctx.rank == 0 else None
+    if ctx.rank == 0:
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": r["dtype"], "data": "synthetic", "samples_per_sec": r["samples_per_sec"],
+                "config": r["config"], "clocks": clk, "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+                "gpu_launches_note": r["gpu_launches_note"], "roofline": r["roofline"], "losses": r["losses"]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def main():

@@ -15,7 +15,10 @@
  *     legacy default stream).  No entry point synchronises the device.
  *   - Return value: 0 on success, negative VAE_ERR_* otherwise; the message is
  *     available from vae_last_error() (thread-local).
- *   - No global mutable state: re-entrant across host threads / streams / devices.
+ *   - No global mutable state besides CUDA's per-device function attributes, which are only ever
+ *     set to the same constants (maximum dynamic shared memory): re-entrant across host threads /
+ *     streams.  Launch-shaping environment knobs (VAE_SMALL_*, VAE_MLP_CLUSTER, VAE_TC_CLUSTER) are
+ *     read when a pack is prepared / a GEMM is launched.
  *   - There is no CPU fallback anywhere behind this header.
  *
  * Tensors are float32 row-major; PRNG keys are uint32[2] (jax.random legacy
@@ -31,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VAE_B200_ABI_VERSION 2
+#define VAE_B200_ABI_VERSION 3
 #define VAE_MAX_HIDDEN 8
 
 enum {
@@ -180,6 +183,10 @@ typedef struct VaeTrainJob {
   void* workspace;          /* vae_train_fused_workspace_bytes(job) bytes, or NULL if 0 */
 } VaeTrainJob;
 
+/* Note on padding rows: generated batches have exactly-zero padding columns, so the fused kernels skip
+ * the encoder-kernel rows that multiply them (gradient exactly 0).  If the caller supplies NON-zero Adam
+ * moments for those rows (e.g. a checkpoint of a -dn noisy run) the kernels detect it at launch and apply
+ * the g = 0 Adam update to them every step, exactly like flax Adam / vae_adam_update would. */
 /* >0 if a fused persistent kernel exists for this job's shape (1 = single-CTA
  * kernel, 2 = thread-block-cluster kernel), else 0. */
 int vae_train_fused_supported(const VaeTrainJob* job);
@@ -198,6 +205,32 @@ size_t vae_train_fused_scratch_bytes(int32_t n_jobs);
  * launch has completed). */
 int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
                     size_t scratch_bytes, void* stream);
+
+/* Prepared pack: the same persistent launch with every per-job cost paid ONCE.  vae_pack_prepare
+ * validates the jobs, copies the device job table into d_scratch (on `stream`) and records the launch
+ * plan (kernel class, models per CTA / cluster size, shared-memory size; the environment knobs are read
+ * here) in the caller-owned POD `plan`; vae_pack_train(plan, n_steps) is then exactly ONE kernel launch
+ * with no host-side per-job work, so short chunks (tens of steps) are not host-bound.  The plan holds
+ * d_scratch and the jobs' device pointers: all of them must stay alive and unmoved while it is used.
+ * vae_train_fused(...) == vae_pack_prepare(...) followed by vae_pack_train(...).
+ * Replaces the loop body model.py:221-222 as called from model.py:213 (one call per chunk of the loop). */
+typedef struct VaePackPlan {
+  int32_t abi;            /* VAE_B200_ABI_VERSION the plan was built by            */
+  int32_t cls;            /* vae_train_fused_supported() class of the pack          */
+  int32_t n_jobs;
+  int32_t shape_id;       /* class 1: kernel instance                               */
+  int32_t homogeneous;    /* class 1: every job has the same shape and batch        */
+  int32_t gm;             /* class 1: models per CTA                                */
+  int32_t cluster;        /* CTAs per thread-block cluster                          */
+  int32_t nbuf;           /* class 1: eps buffers (2 = drawn one step ahead)        */
+  uint64_t smem_bytes;    /* dynamic shared memory per CTA                          */
+  void* d_jobs;           /* device job table (= d_scratch)                         */
+  int32_t device;         /* CUDA device the plan was prepared on                   */
+  int32_t reserved_[5];
+} VaePackPlan;
+int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, size_t scratch_bytes,
+                     VaePackPlan* plan, void* stream);
+int vae_pack_train(const VaePackPlan* plan, int64_t n_steps, void* stream);
 
 /* ------------------------------------------------- tensor-core GEMM building blocks
  * Used by the per-op step when a Dense layer is a true dense contraction (configs[4]:

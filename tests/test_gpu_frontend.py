@@ -144,8 +144,8 @@ def test_bench_b200_arm_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "300", "--warmup", "3", "--cpu-seconds", "1"],
-                         capture_output=True, text=True, timeout=600, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "20", "--warmup", "5", "--cpu-seconds", "1",
+                          "--dp-steps", "1"], capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -153,8 +153,16 @@ def test_bench_b200_arm_contract():
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
-    assert d["steps"] == 300 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["value"] > 0
-    assert d["gpu_launches"] == 1                                   # one persistent launch in the timed region
+    assert d["steps"] == 20 and d["warmup"] == 5 and d["n_gpus"] == 1 and d["value"] > 0
+    # one persistent launch per repeat of the K-step unit; the window is >= 50 ms of back-to-back launches
+    assert d["gpu_launches"] == d["timing"]["repeats"] >= 3 and d["timing"]["window_ms"] >= 45.0
+    assert abs(d["ms_per_step"] - d["timing"]["launch_ms_median"] / 20) < 1e-12
+    # the other BASELINE.json configs ride in the same line, each with its own roofline
+    assert set(d["sub_results"]) == {"single_chain", "sphere_pack", "sphere_single_chain", "sweep_mix_54_runs", "cfg5_sphere_dp"}
+    for name, sub in d["sub_results"].items():
+        assert sub["value"] > 0 and sub["ms_per_step"] > 0, name
+        assert set(sub["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}, name
+    assert d["sub_results"]["cfg5_sphere_dp"]["roofline"]["bound"] == "tensor"
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0

@@ -480,6 +480,58 @@ def test_fused_fixed_variance_and_odd_batch(ops, lib):
         assert_params_close(st["P"].cpu().numpy(), tr.params, n, d.lr)
 
 
+def test_pack_plan_equals_train_fused(ops, lib):
+    """vae_pack_prepare once + vae_pack_train per chunk == vae_train_fused per chunk, bit for bit (the plan
+    only hoists validation / job-table upload out of the launch), for a class-1 pack and a class-2 model."""
+    n_jobs = 8
+    packs = []
+    for _ in range(2):
+        packs.append([fused_setup(ops, lib, FUSED_CASES[7][:6] + (69 + i,), 40) for i in range(n_jobs)])
+    sc_a, sc_b = ops.fused_scratch(n_jobs), ops.fused_scratch(n_jobs)
+    plan = ops.pack_prepare([p[4] for p in packs[1]], sc_b)
+    assert plan.cls == 1 and plan.n_jobs == n_jobs and plan.abi == lib.load().vae_abi_version()
+    for chunk in (3, 17, 20):
+        ops.train_fused([p[4] for p in packs[0]], chunk, sc_a)
+        ops.pack_train(plan, chunk)
+    torch.cuda.synchronize()
+    for a, b in zip(packs[0], packs[1]):
+        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+            assert torch.equal(a[3][k], b[3][k]), k
+    # a stale / foreign plan is refused
+    bad = type(plan)()
+    with pytest.raises(lib.VaeB200Error):
+        ops.pack_train(bad, 1)
+
+
+@pytest.mark.parametrize("case_idx", [0, 8, 12])
+def test_fused_small_nonzero_moments_on_padding_rows(ops, lib, case_idx):
+    """Caller-supplied state with NON-zero Adam moments on the encoder rows that multiply the zero padding
+    columns (e.g. a checkpoint of a -dn noisy run): flax Adam keeps moving those weights while m != 0
+    (gradient exactly 0), and so must the fused kernel -- compared with the oracle's dense Adam."""
+    n = 24
+    case = FUSED_CASES[case_idx]
+    d, ds, tr, st, job = fused_setup(ops, lib, case, n)
+    rng = np.random.default_rng(5)
+    m0 = (rng.standard_normal(d.n_params) * 1e-2).astype(np.float32)
+    v0 = (rng.random(d.n_params) * 1e-4).astype(np.float32)
+    tr.m[:] = m0
+    tr.v[:] = v0
+    st["M"].copy_(dev(m0))
+    st["V"].copy_(dev(v0))
+    dr = case[1] + (1 if case[0] == "sigmoid" else 0)
+    pad_rows = slice(dr * d.latent_dim, d.data_dim * d.latent_dim)          # encoder kernel rows d >= DR
+    p_before = st["P"].cpu().numpy().copy()
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    got = st["P"].cpu().numpy()
+    assert np.abs(got[pad_rows] - p_before[pad_rows]).max() > 1e-4         # they did move
+    np.testing.assert_allclose(got[pad_rows], tr.params[pad_rows], rtol=0, atol=n * 1e-3 * d.lr)
+    assert relerr(st["M"].cpu().numpy()[pad_rows], tr.m[pad_rows]) <= 1e-5
+    assert relerr(st["V"].cpu().numpy()[pad_rows], tr.v[pad_rows]) <= 1e-5
+    assert_params_close(got, tr.params, n, d.lr)
+
+
 def test_fused_unsupported_shape_is_refused(ops, lib):
     d = vs.VaeDesc(100, 9, 5)
     P = torch.zeros(d.n_params, device="cuda")
@@ -612,6 +664,31 @@ def test_fused_cluster_vs_oracle_loop(ops, lib, case):
     assert_params_close(st["P"].cpu().numpy(), tr.params, n, d.lr, frac=0.95)
     assert relerr(st["M"].cpu().numpy(), tr.m) <= 1e-4
     assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
+
+
+def test_fused_cluster_nonzero_moments_on_padding_rows(ops, lib):
+    """As test_fused_small_nonzero_moments_on_padding_rows, for the cluster kernel: encoder layer-0 rows that
+    multiply the zero padding columns keep decaying under flax Adam when their moments are non-zero."""
+    n = 8
+    case = MLP_CASES[1]                                   # dd=3, pd=13: 13 padding rows x 200 columns
+    d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
+    rng = np.random.default_rng(9)
+    m0 = (rng.standard_normal(d.n_params) * 1e-2).astype(np.float32)
+    v0 = (rng.random(d.n_params) * 1e-4).astype(np.float32)
+    tr.m[:] = m0
+    tr.v[:] = v0
+    st["M"].copy_(dev(m0))
+    st["V"].copy_(dev(v0))
+    pad_rows = slice(case[1] * 200, d.data_dim * 200)
+    p_before = st["P"].cpu().numpy().copy()
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    got = st["P"].cpu().numpy()
+    assert np.abs(got[pad_rows] - p_before[pad_rows]).max() > 1e-5
+    np.testing.assert_allclose(got[pad_rows], tr.params[pad_rows], rtol=0, atol=n * 1e-3 * d.lr)
+    assert relerr(st["M"].cpu().numpy()[pad_rows], tr.m[pad_rows]) <= 1e-5
+    assert relerr(st["V"].cpu().numpy()[pad_rows], tr.v[pad_rows]) <= 1e-5
 
 
 def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):

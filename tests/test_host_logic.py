@@ -114,7 +114,7 @@ def test_builtin_sweeps_match_reference_scripts():
     if not os.path.isdir(ref_dir):
         pytest.skip("reference tree not available")
     key = lambda a: (a.dataset, a.dataset_dimension, a.padding_dim, a.latent_dimension, a.dataset_seed)
-    fields = ("dataset", "dataset_dimension", "padding_dim", "latent_dimension", "dataset_seed", "num_batches",
+    fields = ("name", "dataset", "dataset_dimension", "padding_dim", "latent_dimension", "dataset_seed", "num_batches",
               "learning_rate", "epsilon", "tunable_decoder_var", "layer_sizes", "encoder_layer_sizes", "batch_size",
               "overwrite")
     for which, fn in (("linear", "seed_linpadding_expts.sh"), ("sigmoid", "sigmoid_vae_padding_expts.sh"),

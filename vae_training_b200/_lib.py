@@ -45,6 +45,15 @@ class VaeTrainJob(C.Structure):
     ]
 
 
+class VaePackPlan(C.Structure):
+    """Caller-owned launch plan of a prepared pack (include/vae_b200.h: VaePackPlan)."""
+    _fields_ = [
+        ("abi", C.c_int32), ("cls", C.c_int32), ("n_jobs", C.c_int32), ("shape_id", C.c_int32),
+        ("homogeneous", C.c_int32), ("gm", C.c_int32), ("cluster", C.c_int32), ("nbuf", C.c_int32),
+        ("smem_bytes", C.c_uint64), ("d_jobs", C.c_void_p), ("device", C.c_int32), ("reserved_", C.c_int32 * 5),
+    ]
+
+
 _P = C.c_void_p
 _PROTOTYPES = {
     "vae_param_count": (C.c_int64, [C.POINTER(VaeDesc)]),
@@ -71,6 +80,8 @@ _PROTOTYPES = {
     "vae_train_fused_resident_jobs": (C.c_int, [C.POINTER(VaeTrainJob)]),
     "vae_train_fused_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "vae_train_fused": (C.c_int, [C.POINTER(VaeTrainJob), C.c_int32, C.c_int64, _P, C.c_size_t, _P]),
+    "vae_pack_prepare": (C.c_int, [C.POINTER(VaeTrainJob), C.c_int32, _P, C.c_size_t, C.POINTER(VaePackPlan), _P]),
+    "vae_pack_train": (C.c_int, [C.POINTER(VaePackPlan), C.c_int64, _P]),
     "vae_split_tf32": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "vae_transpose_split_tf32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "vae_gemm_nt_3xtf32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_int64, _P,

@@ -1,6 +1,7 @@
 // fused_api.cu -- the fused-training entry points of the C ABI: dispatch between the
 // single-CTA kernel (fused_small.cu, class 1) and the cluster kernel (fused_mlp.cu, class 2).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -9,13 +10,15 @@ namespace vae {
 int small_supported(const VaeTrainJob* job);
 int small_ctas_per_sm(const VaeTrainJob* job);
 size_t small_job_bytes();
-int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch, cudaStream_t s);
+int small_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, cudaStream_t s, VaePackPlan* plan);
+int small_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
 // fused_mlp.cu
 struct MlpJobDev;
 int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes, size_t* smem4 = nullptr);
 int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o);
 size_t mlp_job_bytes();
-int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_t n_steps, cudaStream_t s);
+int mlp_prepare(int n_jobs, size_t smem, size_t smem4, VaePackPlan* plan);
+int mlp_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
 int mlp_resident_jobs(size_t smem, size_t smem4, int* out);
 }  // namespace vae
 
@@ -61,51 +64,79 @@ size_t vae_train_fused_scratch_bytes(int32_t n_jobs) {
   return n_jobs > 0 ? (size_t)n_jobs * per : 0;
 }
 
-int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
-                    size_t scratch_bytes, void* stream) {
-  VAE_REQUIRE(jobs && n_jobs > 0 && n_steps >= 0, "vae_train_fused: bad arguments");
+int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, size_t scratch_bytes,
+                     VaePackPlan* plan, void* stream) {
+  VAE_REQUIRE(jobs && n_jobs > 0 && plan, "vae_pack_prepare: bad arguments");
   VAE_REQUIRE(d_scratch && scratch_bytes >= vae_train_fused_scratch_bytes(n_jobs),
-              "vae_train_fused: scratch too small (need %zu bytes)", vae_train_fused_scratch_bytes(n_jobs));
-  if (n_steps == 0) return 0;
+              "vae_pack_prepare: scratch too small (need %zu bytes)", vae_train_fused_scratch_bytes(n_jobs));
   cudaStream_t s = (cudaStream_t)stream;
+  memset(plan, 0, sizeof(*plan));
   const int cls = vae_train_fused_supported(&jobs[0]);
   for (int i = 0; i < n_jobs; ++i) {
     const int c = vae_train_fused_supported(&jobs[i]);
     if (c == 0) {
-      vae::set_error("vae_train_fused: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i, jobs[i].desc.data_dim,
+      vae::set_error("vae_pack_prepare: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i, jobs[i].desc.data_dim,
                      jobs[i].desc.latent_dim, jobs[i].desc.n_enc_hidden, jobs[i].desc.n_dec_hidden);
       return VAE_ERR_UNSUPPORTED;
     }
-    VAE_REQUIRE(c == cls, "vae_train_fused: jobs %d and 0 belong to different fused-kernel classes (%d vs %d)", i, c, cls);
+    VAE_REQUIRE(c == cls, "vae_pack_prepare: jobs %d and 0 belong to different fused-kernel classes (%d vs %d)", i, c, cls);
   }
-  if (cls == 1) return vae::small_train_fused(jobs, n_jobs, n_steps, d_scratch, s);
-
-  // class 2: one cluster per model
-  const size_t jb = vae::mlp_job_bytes();
-  char* host = (char*)malloc((size_t)n_jobs * jb);
-  VAE_REQUIRE(host, "vae_train_fused: out of host memory");
-  size_t smem = 0, smem4 = 0;
-  bool ok4 = true;
-  for (int i = 0; i < n_jobs; ++i) {
-    const VaeTrainJob& j = jobs[i];
-    size_t sb = 0, wb = 0, s4 = 0;
-    vae::mlp_supported(&j, &sb, &wb, &s4);
-    if (s4 == 0) ok4 = false; else if (s4 > smem4) smem4 = s4;
-    if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
-        !j.workspace || (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
-      free(host);
-      vae::set_error("vae_train_fused: job %d has a NULL device pointer (class 2 needs a workspace of "
-                     "vae_train_fused_workspace_bytes() = %zu bytes)", i, wb);
-      return VAE_ERR_INVALID;
+  int dev = 0;
+  VAE_CUDA_OK(cudaGetDevice(&dev));
+  int rc;
+  if (cls == 1) {
+    if ((rc = vae::small_prepare(jobs, n_jobs, d_scratch, s, plan))) return rc;
+  } else {
+    // class 2: one cluster per model
+    const size_t jb = vae::mlp_job_bytes();
+    char* host = (char*)malloc((size_t)n_jobs * jb);
+    VAE_REQUIRE(host, "vae_pack_prepare: out of host memory");
+    size_t smem = 0, smem4 = 0;
+    bool ok4 = true;
+    for (int i = 0; i < n_jobs; ++i) {
+      const VaeTrainJob& j = jobs[i];
+      size_t sb = 0, wb = 0, s4 = 0;
+      vae::mlp_supported(&j, &sb, &wb, &s4);
+      if (s4 == 0) ok4 = false; else if (s4 > smem4) smem4 = s4;
+      if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
+          !j.workspace || (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
+        free(host);
+        vae::set_error("vae_pack_prepare: job %d has a NULL device pointer (class 2 needs a workspace of "
+                       "vae_train_fused_workspace_bytes() = %zu bytes)", i, wb);
+        return VAE_ERR_INVALID;
+      }
+      if (sb > smem) smem = sb;
+      rc = vae::mlp_fill_job(j, (vae::MlpJobDev*)(host + (size_t)i * jb));
+      if (rc) { free(host); return rc; }
     }
-    if (sb > smem) smem = sb;
-    int rc = vae::mlp_fill_job(j, (vae::MlpJobDev*)(host + (size_t)i * jb));
-    if (rc) { free(host); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * jb, cudaMemcpyHostToDevice, s);
+    free(host);
+    VAE_CUDA_OK(e);
+    plan->cls = 2; plan->n_jobs = n_jobs; plan->d_jobs = d_scratch;
+    if ((rc = vae::mlp_prepare(n_jobs, smem, ok4 ? smem4 : 0, plan))) return rc;
   }
-  cudaError_t e = cudaMemcpyAsync(d_scratch, host, (size_t)n_jobs * jb, cudaMemcpyHostToDevice, s);
-  free(host);
-  VAE_CUDA_OK(e);
-  return vae::mlp_launch(d_scratch, n_jobs, smem, ok4 ? smem4 : 0, n_steps, s);
+  plan->abi = VAE_B200_ABI_VERSION;
+  plan->device = dev;
+  return 0;
+}
+
+int vae_pack_train(const VaePackPlan* plan, int64_t n_steps, void* stream) {
+  VAE_REQUIRE(plan && plan->abi == VAE_B200_ABI_VERSION && plan->d_jobs && plan->n_jobs > 0 && n_steps >= 0,
+              "vae_pack_train: plan was not produced by vae_pack_prepare of this library version");
+  if (n_steps == 0) return 0;
+  if (plan->cls == 1) return vae::small_launch(plan, n_steps, (cudaStream_t)stream);
+  if (plan->cls == 2) return vae::mlp_launch(plan, n_steps, (cudaStream_t)stream);
+  vae::set_error("vae_pack_train: bad plan class %d", plan->cls);
+  return VAE_ERR_INVALID;
+}
+
+int vae_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch,
+                    size_t scratch_bytes, void* stream) {
+  VAE_REQUIRE(jobs && n_jobs > 0 && n_steps >= 0, "vae_train_fused: bad arguments");
+  if (n_steps == 0) return 0;
+  VaePackPlan plan;
+  const int rc = vae_pack_prepare(jobs, n_jobs, d_scratch, scratch_bytes, &plan, stream);
+  return rc ? rc : vae_pack_train(&plan, n_steps, stream);
 }
 
 }  // extern "C"

@@ -315,7 +315,14 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   double b1t = pow((double)J.b1, (double)step0), b2t = pow((double)J.b2, (double)step0);
   MlpHyper hp; hp.lr = J.lr; hp.b1 = J.b1; hp.b2 = J.b2; hp.omb1 = J.omb1; hp.omb2 = J.omb2; hp.eps = J.adam_eps;
   const float invB = 1.0f / (float)B, fB = (float)B;
-  __syncthreads();
+  // Encoder layer 0 rows d >= DR multiply exactly-zero padding columns (gradient exactly 0): with zero Adam
+  // moments flax Adam leaves them unchanged and they are never touched.  A caller-supplied state with
+  // NON-zero moments there still decays: CTA 0 then applies the g = 0 Adam update to those rows every step.
+  const int skip0 = J.enc_w[0] + DR * J.enc_sizes[1], skipN = (D - DR) * J.enc_sizes[1];
+  int nz = 0;
+  if (rank == 0)
+    for (int g = tid; g < skipN; g += kMT) nz |= (J.adam_m[skip0 + g] != 0.f || J.adam_v[skip0 + g] != 0.f) ? 1 : 0;
+  const bool decay_skipped = __syncthreads_or(nz) != 0;
   cluster_barrier();
 
   for (int64_t s = 0; s < n_steps; ++s) {
@@ -533,6 +540,8 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
       cp_async_wait_all(); __syncthreads();
     }
+    if (decay_skipped)
+      for (int g = tid; g < skipN; g += kMT) adam_one(J.params, J.adam_m, J.adam_v, (size_t)skip0 + g, 0.f, hp);
     // the next step's phase-R barrier orders this step's parameter writes before any read
   }
   cluster_barrier();
@@ -619,9 +628,15 @@ int mlp_fill_job(const VaeTrainJob& j, MlpJobDev* o) {
 
 size_t mlp_job_bytes() { return sizeof(MlpJobDev); }
 
+// Function attributes are only ever set to the same constants (see fused_small.cu:set_kernel_attrs).
+static int mlp_set_attrs() {
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  return 0;
+}
+
 static int mlp_active_clusters(int cs, size_t smem, int* out) {
-  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (int rc = mlp_set_attrs()) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * 64, 1, 1);
   cfg.blockDim = dim3(kMT, 1, 1);
@@ -676,21 +691,27 @@ static int mlp_pick_cluster(int n_jobs, size_t smem, size_t smem4) {
   return 1;
 }
 
-int mlp_launch(const void* d_jobs, int n_jobs, size_t smem, size_t smem4, int64_t n_steps, cudaStream_t s) {
+// Chooses the cluster size for the pack (occupancy queries, environment) -- once, at prepare time.
+int mlp_prepare(int n_jobs, size_t smem, size_t smem4, VaePackPlan* plan) {
+  if (int rc = mlp_set_attrs()) return rc;
   const int cs = mlp_pick_cluster(n_jobs, smem, smem4);
   if (cs <= kMlpSmallCluster) smem = smem4;
-  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cs > 8) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  plan->cluster = cs; plan->smem_bytes = (uint64_t)smem;
+  return 0;
+}
+
+int mlp_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s) {
+  const int cs = plan->cluster;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_jobs * cs), 1, 1);
+  cfg.gridDim = dim3((unsigned)(plan->n_jobs * cs), 1, 1);
   cfg.blockDim = dim3(kMT, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = (size_t)plan->smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = cs > 1 ? 1 : 0;
-  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)d_jobs, n_steps));
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_kernel, (const MlpJobDev*)plan->d_jobs, n_steps));
   count_launch();
   return 0;
 }

@@ -268,11 +268,21 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     const int o = C::padded_of(g, tunable);
     if (o >= 0) { P[o] = job.params[g]; M[o] = job.adam_m[g]; V[o] = job.adam_v[g]; }
   }
+  // Encoder kernel rows d >= DR (flat [DR*L, D*L)) multiply exactly-zero padding columns: their gradient
+  // is exactly 0 and, with zero Adam moments, flax Adam leaves them unchanged -- they are never loaded.
+  // A caller-supplied state with NON-zero moments there (e.g. a checkpoint of a noisy-padding run) still
+  // decays: those rows then take the g = 0 Adam update in global memory every step (rare, slow, exact).
+  constexpr int kSkip0 = DR * L, kSkipN = (D - DR) * L;
+  if constexpr (kSkipN > 0) {
+    for (int g = t; g < kSkipN; g += kT)
+      if (job.adam_m[kSkip0 + g] != 0.f || job.adam_v[kSkip0 + g] != 0.f) sm[y.red + 12] = 1.0f;   // benign race: all store 1
+  }
   for (int i = t; i < C::AN; i += kT) sm[y.A + i] = job.A[i];
   for (int b = t; b < B; b += kT) { sm[y.hx + DR * BP + b] = 1.0f; sm[y.hz + L * BP + b] = 1.0f; }   // ones rows
   __syncthreads();
   // Derived per-step constants are double-buffered by step parity: phase B/C of step s
   // read slot s&1, the owning thread publishes the post-update values into the other slot.
+  const bool decay_skipped = kSkipN > 0 && sm[y.red + 12] != 0.f;
   if (t < L) {
     const float lv = P[C::oLv + t], elv = expf(lv);
     sm[y.sl + t] = expf(0.5f * lv); sm[y.el + t] = elv;
@@ -523,6 +533,17 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
           scn[0] = e2; scn[1] = expf(0.5f * e2); scn[2] = expf(-e2);
         }
       }
+      if constexpr (kSkipN > 0) {
+        if (decay_skipped) {          // g = 0 Adam on the never-loaded encoder rows (same arithmetic as adam())
+          for (int g = t; g < kSkipN; g += kT) {
+            const int gi = kSkip0 + g;
+            const float m = job.b1 * job.adam_m[gi] + job.omb1 * 0.f;
+            const float v = job.b2 * job.adam_v[gi] + job.omb2 * 0.f * 0.f;
+            job.adam_m[gi] = m; job.adam_v[gi] = v;
+            job.params[gi] = job.params[gi] - __fdividef(job.lr * (m * ibc1), approx_sqrt(v * ibc2) + job.adam_eps);
+          }
+        }
+      }
 #pragma unroll 1
       for (int rnd = 0; rnd < C::ROUNDS; ++rnd) {
         if (rnd * kT + (t & ~31) >= C::NTASK) break;                    // warp-uniform
@@ -733,11 +754,20 @@ static SmallPlan plan_small(const VaeTrainJob* job0, int n_jobs, bool homogeneou
   return p;
 }
 
+// Function attributes are per-device mutable state shared by every host thread: they are only ever set
+// to the SAME constants (the 227 KB maximum, carve-out 100), at prepare time, so concurrent packs of one
+// kernel with different shared-memory needs cannot race; the launch itself passes its own size.
 template <class K>
-static int launch_one(K k, int n_ctas, int threads, int cluster, size_t smem, const FusedJobDev* d_jobs, int64_t n_steps,
-                      cudaStream_t s) {
-  VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int set_kernel_attrs(K k) {
+  VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  return 0;
+}
+
+template <class K>
+static int launch_one(K k, bool prepare_only, int n_ctas, int threads, int cluster, size_t smem, const FusedJobDev* d_jobs,
+                      int64_t n_steps, cudaStream_t s) {
+  if (prepare_only) return set_kernel_attrs(k);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_ctas, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
@@ -751,8 +781,9 @@ static int launch_one(K k, int n_ctas, int threads, int cluster, size_t smem, co
   return 0;
 }
 
+// prepare_only: set the kernel's function attributes (vae_pack_prepare); otherwise launch (vae_pack_train)
 static int launch_small(int shape_id, bool homogeneous, const SmallPlan& p, int n_jobs, const FusedJobDev* d_jobs,
-                        int64_t n_steps, cudaStream_t s) {
+                        int64_t n_steps, cudaStream_t s, bool prepare_only) {
   if (homogeneous) {
     int rc = 0;
     switch (shape_id) {
@@ -760,19 +791,18 @@ static int launch_small(int shape_id, bool homogeneous, const SmallPlan& p, int 
       case id:                                                                                             \
         if (p.gm == kGM)                                                                                   \
           rc = launch_one(fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, kGM>,           \
-                          n_jobs / kGM, kT * kGM, 1, p.smem, d_jobs, n_steps, s);                          \
+                          prepare_only, n_jobs / kGM, kT * kGM, 1, p.smem, d_jobs, n_steps, s);            \
         else                                                                                               \
-          rc = launch_one(fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1>, n_jobs, kT, \
-                          p.cluster, p.smem, d_jobs, n_steps, s);                                          \
+          rc = launch_one(fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1>,             \
+                          prepare_only, n_jobs, kT, p.cluster, p.smem, d_jobs, n_steps, s);                \
         break;
       VAE_SMALL_SHAPES(X)
 #undef X
       default: set_error("bad shape id %d", shape_id); return VAE_ERR_INVALID;
     }
-    if (rc) return rc;
+    if (rc || prepare_only) return rc;
   } else {
-    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    VAE_CUDA_OK(cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (prepare_only) return set_kernel_attrs(fused_small_kernel);
     fused_small_kernel<<<n_jobs, kT, p.smem, s>>>(d_jobs, n_steps);
   }
   VAE_LAUNCH_OK("fused_small_kernel");
@@ -787,13 +817,11 @@ static int occupancy_small(int shape_id, const SmallPlan& p, int* out) {
     case id: {                                                                                             \
       if (p.gm == kGM) {                                                                                   \
         auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, kGM>;                    \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));    \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        if (int rc_ = set_kernel_attrs(k)) return rc_;                                                     \
         VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kT * kGM, p.smem));          \
       } else {                                                                                             \
         auto k = fused_small_kernel_one<SmallCfg<D, L, DR, SIG, KIND, G, TI, TJ>, 1>;                      \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));    \
-        VAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        if (int rc_ = set_kernel_attrs(k)) return rc_;                                                     \
         VAE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kT, p.smem));                \
       }                                                                                                    \
       break;                                                                                               \
@@ -831,9 +859,11 @@ int small_supported(const VaeTrainJob* job) {
 
 size_t small_job_bytes() { return sizeof(FusedJobDev); }
 
-int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, void* d_scratch, cudaStream_t s) {
+// Validates the jobs, uploads the device job table into d_scratch (on `s`) and records how the pack
+// will be launched.  Everything per-job happens here, once; small_launch is a bare kernel launch.
+int small_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, cudaStream_t s, VaePackPlan* plan) {
   FusedJobDev* host = (FusedJobDev*)malloc((size_t)n_jobs * sizeof(FusedJobDev));
-  VAE_REQUIRE(host, "vae_train_fused: out of host memory");
+  VAE_REQUIRE(host, "vae_pack_prepare: out of host memory");
   int max_fl = 0;
   bool homogeneous = true;
   for (int i = 0; i < n_jobs; ++i) {
@@ -842,14 +872,14 @@ int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, 
     const int id = small_shape_of(&j, &fl);
     if (id < 0 || (size_t)fl * 4 > (size_t)kMaxSmem) {
       free(host);
-      set_error("vae_train_fused: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i,
+      set_error("vae_pack_prepare: job %d has no fused kernel (D=%d L=%d hidden=%d/%d)", i,
                      j.desc.data_dim, j.desc.latent_dim, j.desc.n_enc_hidden, j.desc.n_dec_hidden);
       return VAE_ERR_UNSUPPORTED;
     }
     if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
         (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
       free(host);
-      set_error("vae_train_fused: job %d has a NULL device pointer", i);
+      set_error("vae_pack_prepare: job %d has a NULL device pointer", i);
       return VAE_ERR_INVALID;
     }
     if (fl > max_fl) max_fl = fl;
@@ -870,7 +900,16 @@ int small_train_fused(const VaeTrainJob* jobs, int32_t n_jobs, int64_t n_steps, 
   VAE_CUDA_OK(e);
   SmallPlan p = plan_small(&jobs[0], n_jobs, homogeneous);
   if (!homogeneous) p.smem = (size_t)max_fl * sizeof(float);
-  return launch_small(shape0, homogeneous, p, n_jobs, (const FusedJobDev*)d_scratch, n_steps, s);
+  plan->cls = 1; plan->n_jobs = n_jobs; plan->shape_id = shape0; plan->homogeneous = homogeneous ? 1 : 0;
+  plan->gm = p.gm; plan->cluster = p.cluster; plan->nbuf = p.nbuf; plan->smem_bytes = (uint64_t)p.smem;
+  plan->d_jobs = d_scratch;
+  return launch_small(shape0, homogeneous, p, n_jobs, (const FusedJobDev*)d_scratch, 0, s, /*prepare_only=*/true);
+}
+
+int small_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s) {
+  SmallPlan p = {plan->gm, plan->cluster, plan->nbuf, (size_t)plan->smem_bytes};
+  return launch_small(plan->shape_id, plan->homogeneous != 0, p, plan->n_jobs, (const FusedJobDev*)plan->d_jobs, n_steps, s,
+                      /*prepare_only=*/false);
 }
 
 }  // namespace vae

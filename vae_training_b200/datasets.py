@@ -50,7 +50,9 @@ class DistributionDataset:
         return (samps, None) if return_latents else samps
 
     def _scores(self, batch):
-        return ops.dataset_score(self.data_desc(), self.A, batch.contiguous()).cpu().numpy()
+        """Device float32[2]; nothing is read back here (a ``.cpu()`` per model per eval event would
+        stall the stream between two persistent launches) -- ``VAEModel.write_stats`` defers it."""
+        return ops.dataset_score(self.data_desc(), self.A, batch.contiguous())
 
     def plot_batch(self, batch, fn=None):
         """PNG output is out of scope; RNG side effects are kept."""

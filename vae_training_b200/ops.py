@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import VaeB200Error, VaeDataDesc, VaeDesc, VaeTrainJob, check
+from ._lib import VaeB200Error, VaeDataDesc, VaeDesc, VaePackPlan, VaeTrainJob, check
 
 
 def _stream() -> C.c_void_p:
@@ -236,6 +236,23 @@ def train_fused(jobs: Sequence[VaeTrainJob], n_steps: int, scratch: torch.Tensor
     arr = (VaeTrainJob * n)(*jobs)
     check(_lib.load().vae_train_fused(arr, n, int(n_steps), _ptr(scratch), C.c_size_t(scratch.numel() * scratch.element_size()),
                                       _stream()), "vae_train_fused")
+
+
+def pack_prepare(jobs: Sequence[VaeTrainJob], scratch: torch.Tensor) -> VaePackPlan:
+    """Validates the jobs and uploads their device job table ONCE (vae_pack_prepare); the returned
+    plan makes every later ``pack_train`` a single kernel launch with no per-job host work.  The
+    caller keeps ``scratch`` and every tensor the jobs point to alive while the plan is in use."""
+    n = len(jobs)
+    arr = (VaeTrainJob * n)(*jobs)
+    plan = VaePackPlan()
+    check(_lib.load().vae_pack_prepare(arr, n, _ptr(scratch), C.c_size_t(scratch.numel() * scratch.element_size()),
+                                       C.byref(plan), _stream()), "vae_pack_prepare")
+    return plan
+
+
+def pack_train(plan: VaePackPlan, n_steps: int):
+    """n_steps hot-loop iterations (model.py:221-222) of every job of the prepared pack: ONE launch."""
+    check(_lib.load().vae_pack_train(C.byref(plan), int(n_steps), _stream()), "vae_pack_train")
 
 
 def fused_scratch(n_jobs: int, device="cuda") -> torch.Tensor:

@@ -106,28 +106,36 @@ class PackedRuns:
         self.a_sizes = a_sizes
         self.a_off, atot = _offsets(a_sizes)
         dev = self.device
-        # flat device buffers (16-byte aligned slices per model)
-        self.P = torch.zeros(ptot, dtype=torch.float32, device=dev)
-        self.Mo = torch.zeros(ptot, dtype=torch.float32, device=dev)
-        self.V = torch.zeros(ptot, dtype=torch.float32, device=dev)
-        self.A = torch.zeros(max(atot, 4), dtype=torch.float32, device=dev)
-        self.step = torch.zeros(self.M * 4, dtype=torch.int32, device=dev)        # stride 4: 16-byte slots
-        self.keys = torch.zeros(self.M * 8, dtype=torch.uint32, device=dev)       # [model_key(2) pad(2) dataset_key(2) pad(2)]
-        self.loss = torch.zeros(self.M * self.max_chunk, dtype=torch.float32, device=dev)
-        self.scratch = ops.fused_scratch(self.M, dev)
-        # pinned host mirrors for the end-to-end path
+        # ONE device arena and ONE pinned host mirror, laid out [P | M | V | A | step | keys | loss] (every
+        # segment 16-byte aligned, all 4-byte element types), so the end-to-end path moves the whole state
+        # with a single H2D copy and state + losses with a single D2H copy.
+        na = max(atot, 4)
+        seg = [("P", ptot), ("Mo", ptot), ("V", ptot), ("A", na), ("step", self.M * 4), ("keys", self.M * 8),
+               ("loss", self.M * self.max_chunk)]
+        offs, words = _offsets([n for _, n in seg])
+        self._seg = {name: (o, n) for (name, n), o in zip(seg, offs)}
+        self._state_words = self._seg["loss"][0]                       # everything before the loss history
+        self.arena = torch.zeros(words, dtype=torch.float32, device=dev)
         pin = torch.cuda.is_available()
-        self.hP = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
-        self.hM = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
-        self.hV = torch.zeros(ptot, dtype=torch.float32, pin_memory=pin)
-        self.hA = torch.zeros(max(atot, 4), dtype=torch.float32, pin_memory=pin)
-        self.hstep = torch.zeros(self.M * 4, dtype=torch.int32, pin_memory=pin)
-        self.hkeys = torch.zeros(self.M * 8, dtype=torch.uint32, pin_memory=pin)
-        self.hloss = torch.zeros(self.M * self.max_chunk, dtype=torch.float32, pin_memory=pin)
+        self.harena = torch.zeros(words, dtype=torch.float32, pin_memory=pin)
+
+        def view(buf, name, dtype):
+            o, n = self._seg[name]
+            return buf[o:o + n].view(dtype)
+        self.P, self.Mo, self.V, self.A = (view(self.arena, k, torch.float32) for k in ("P", "Mo", "V", "A"))
+        self.step = view(self.arena, "step", torch.int32)              # stride 4: 16-byte slots
+        self.keys = view(self.arena, "keys", torch.uint32)             # [model_key(2) pad(2) dataset_key(2) pad(2)]
+        self.loss = view(self.arena, "loss", torch.float32)
+        self.scratch = ops.fused_scratch(self.M, dev)
+        self.hP, self.hM, self.hV, self.hA = (view(self.harena, k, torch.float32) for k in ("P", "Mo", "V", "A"))
+        self.hstep = view(self.harena, "step", torch.int32)
+        self.hkeys = view(self.harena, "keys", torch.uint32)
+        self.hloss = view(self.harena, "loss", torch.float32)
         self.jobs = [self._make_job(i) for i in range(self.M)]
         # class-2 (cluster kernel) jobs need an L2-resident exchange workspace each
         self.workspaces = [ops.fused_workspace(j, dev) for j in self.jobs]
         self.jobs = [self._make_job(i, self.workspaces[i]) for i in range(self.M)]
+        self.plan = None
         unsupported = [i for i, j in enumerate(self.jobs) if ops.fused_supported(j) == 0]
         if unsupported:
             s = self.specs[unsupported[0]]
@@ -187,33 +195,36 @@ class PackedRuns:
             hk[8 * i:8 * i + 2] = st.model_key
             hk[8 * i + 4:8 * i + 6] = st.dataset_key
 
-    def upload(self, states: Sequence[HostState]) -> int:
-        """Host -> device copy of every model's state (async on the current stream).
-        Returns the number of bytes copied."""
+    def stage(self, states: Sequence[HostState]):
+        """Packs the runs' host state into the pinned host arena (host-side only, no copy to the device)."""
         if len(states) != self.M:
-            raise VaeB200Error("upload: one HostState per run is required")
+            raise VaeB200Error("one HostState per run is required")
         self._stage(states)
-        nb = 0
-        for d, h in ((self.P, self.hP), (self.Mo, self.hM), (self.V, self.hV), (self.A, self.hA),
-                     (self.step, self.hstep), (self.keys, self.hkeys)):
-            d.copy_(h, non_blocking=True)
-            nb += h.numel() * h.element_size()
-        return nb
+
+    def upload(self, states: Optional[Sequence[HostState]] = None) -> int:
+        """Host -> device copy of every model's state: ONE async copy of the pinned arena's state part on
+        the current stream (``states`` given: staged into the pinned arena first).  Returns the bytes copied."""
+        if states is not None:
+            self.stage(states)
+        n = self._state_words
+        self.arena[:n].copy_(self.harena[:n], non_blocking=True)
+        return n * 4
 
     def download(self, n_loss: int, states: Optional[Sequence[HostState]] = None) -> int:
-        """Device -> host copy of losses[:n_loss] per model and the full state.  Synchronises
-        the current stream when ``states`` is given (values are unpacked into them)."""
-        nb = 0
-        pairs = [(self.hP, self.P), (self.hM, self.Mo), (self.hV, self.V), (self.hstep, self.step), (self.hkeys, self.keys)]
-        for h, d in pairs:
-            h.copy_(d, non_blocking=True)
-            nb += h.numel() * h.element_size()
-        if n_loss > 0:
-            src = self.loss.view(self.M, self.max_chunk)[:, :n_loss]
-            if n_loss != self.max_chunk:
-                src = src.contiguous()               # compact on the device, then one flat copy
-            self.hloss[:self.M * n_loss].copy_(src.reshape(-1), non_blocking=True)
-            nb += self.M * n_loss * 4
+        """Device -> host copy of the full state and losses[:n_loss] per model (one copy when n_loss is the
+        whole chunk, else state + compacted losses).  Synchronises the current stream when ``states`` is
+        given (values are unpacked into them)."""
+        n = self._state_words
+        if n_loss == self.max_chunk:
+            self.harena.copy_(self.arena, non_blocking=True)
+            nb = self.arena.numel() * 4
+        else:
+            self.harena[:n].copy_(self.arena[:n], non_blocking=True)
+            nb = n * 4
+            if n_loss > 0:
+                src = self.loss.view(self.M, self.max_chunk)[:, :n_loss].contiguous()     # compact on the device
+                self.hloss[:self.M * n_loss].copy_(src.reshape(-1), non_blocking=True)
+                nb += self.M * n_loss * 4
         if states is not None:
             torch.cuda.current_stream().synchronize()
             hP, hM, hV = self.hP.numpy(), self.hM.numpy(), self.hV.numpy()
@@ -232,12 +243,21 @@ class PackedRuns:
         return nb
 
     # compute -----------------------------------------------------------------
+    def prepare(self):
+        """(Re)builds the launch plan: job validation, device job table upload and the launch-shaping
+        environment knobs (VAE_SMALL_GM, VAE_SMALL_CLUSTER, VAE_MLP_CLUSTER) are all evaluated here, once."""
+        self.plan = ops.pack_prepare(self.jobs, self.scratch)
+        return self.plan
+
     def train_steps(self, n_steps: int):
         """n_steps iterations of the hot loop (model.py:221-222) for every packed model, in
-        one persistent launch on the current stream.  Losses land in ``losses(i, n_steps)``."""
+        one persistent launch on the current stream (``vae_pack_train``: no per-job host work).
+        Losses land in ``losses(i, n_steps)``."""
         if n_steps > self.max_chunk:
             raise VaeB200Error(f"n_steps={n_steps} exceeds max_chunk={self.max_chunk}")
-        ops.train_fused(self.jobs, n_steps, self.scratch)
+        if self.plan is None:
+            self.prepare()
+        ops.pack_train(self.plan, n_steps)
 
     def train_host(self, states: Sequence[HostState], n_steps: int):
         """End-to-end: host state in, n_steps fused steps, host state + losses out."""

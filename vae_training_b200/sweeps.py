@@ -32,12 +32,13 @@ def _padding_runs(dataset: str, grid, hidden: str) -> List[List[str]]:
     out = []
     for ds in OTHER_SEEDS:
         for dd, pd, lat in grid:
-            name = f"{dataset}_dd{dd}_pd{pd}_ld_{lat}_eps-3" + ("" if ds == 69 else f"_ds{ds}")
+            # names and flags exactly as the scripts spell them (..._seed24, --dataset_seed 24)
+            name = f"{dataset}_dd{dd}_pd{pd}_ld_{lat}_eps-3" + ("" if ds == 69 else f"_seed{ds}")
             args = [name, "--dataset", dataset, "--encoder_layer_sizes", hidden, "--layer_sizes", hidden, "-ow",
                     "--latent_dim", str(lat), "--padding_dim", str(pd), "-dd", str(dd), "--num_batches", "150000",
                     "--epsilon", "-3", "-tdv"]
             if ds != 69:
-                args += ["-ds", str(ds)]
+                args += ["--dataset_seed", str(ds)]
             out.append(args)
     return out
 

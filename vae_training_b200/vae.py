@@ -4,7 +4,7 @@ constructor arguments, method names, event schedule, stat names and save payload
 
 Every number is computed on the GPU by libvae_b200.  Between two eval events the hot loop
 (model.py:221-222) runs inside ONE persistent fused launch when the model's shape has a
-fused kernel (``vae_train_fused``); otherwise each step is the per-op sequence
+fused kernel (``vae_pack_prepare`` once, ``vae_pack_train`` per chunk); otherwise each step is the per-op sequence
 get_batch -> split -> normal -> vae_train_step, all enqueued without host synchronisation.
 """
 from __future__ import annotations
@@ -98,6 +98,7 @@ class VAEModel:
         if self._fused_ws is not None:
             self._job = ops.make_job(self.desc, dataset.data_desc(), self.params, self.adam_m, self.adam_v, self.step,
                                      self.key, dataset.key, dataset.A, self._chunk_loss, workspace=self._fused_ws)
+        self._plan = None
         # vae_losses interleaves train and eval losses (vae.py:130,136): kept as device pieces
         self._loss_pieces: List[torch.Tensor] = []
         self.var_enc: List[torch.Tensor] = []
@@ -133,7 +134,9 @@ class VAEModel:
             done = 0
             while done < n_steps:
                 c = min(self.n_print, n_steps - done)
-                ops.train_fused([self._job], c, self._scratch)
+                if self._plan is None:          # validation + job-table upload happen once per model
+                    self._plan = ops.pack_prepare([self._job], self._scratch)
+                ops.pack_train(self._plan, c)
                 self._loss_pieces.append(self._chunk_loss[:c].clone())
                 done += c
         else:
@@ -212,7 +215,7 @@ class VAEModel:
         eval_batch = self.dataset.get_batch(self.print_batch_size)
         score = self.dataset.score_batch(eval_batch)
         if self.verbose:
-            print(f"Score for real data: {score}", flush=True)
+            print(f"Score for real data: { {k: float(v) for k, v in score.items()} }", flush=True)
         self.batchnum = 0
 
     def events_at(self, batchnum: int, save=True):
@@ -302,6 +305,7 @@ def train_many(models: Sequence[VAEModel], save=True):
             with torch.cuda.stream(stream):
                 scratch = ops.fused_scratch(len(fused), fused[0].device)
                 b = 0
+                plan, plan_ids = None, None
                 while True:
                     active = [m for m in fused if b < m.num_batches]
                     if not active:
@@ -310,7 +314,10 @@ def train_many(models: Sequence[VAEModel], save=True):
                         m.events_at(b, save=save)
                     nxt = min(m.next_event(b) for m in active)
                     c = nxt - b
-                    ops.train_fused([m._job for m in active], c, scratch)
+                    ids = tuple(id(m) for m in active)
+                    if ids != plan_ids:         # the pack only changes when a run finishes: re-prepare then
+                        plan, plan_ids = ops.pack_prepare([m._job for m in active], scratch), ids
+                    ops.pack_train(plan, c)
                     for m in active:
                         m._loss_pieces.append(m._chunk_loss[:c].clone())
                         m.batchnum = nxt
