@@ -233,16 +233,17 @@ def run_reference(args):
     K = max(1, int(args.steps))
     W = max(3, int(args.warmup))
     rate, _, _ = cpu_oracle_run(workload, n_models, 40, cores, warm_steps=5)         # calibrate
-    K_run = max(1, min(K, int(rate * 60.0 / n_models)))                              # one pass <= ~60 s
-    t_pass = K_run * n_models / rate
-    R = int(min(100000, max(3, math.ceil(2.5 / t_pass))))
-    rate, med, total = cpu_oracle_run(workload, n_models, K_run, cores, warm_steps=min(W, 200), repeats=R)
+    K_run = max(1, min(K, int(rate * 60.0 / n_models)))                              # K steps <= ~60 s
+    R = int(min(100000, max(3, math.ceil(2.5 * rate / (K_run * n_models)))))         # >= 2.5 s of CPU work
+    # R repeats of the K-step unit as ONE call of the port (its threads are spawned once, as a long run would)
+    rate, med, total = cpu_oracle_run(workload, n_models, K_run * R, cores, warm_steps=min(W, 200))
+    med /= R
     pack = args.models if args.models > 0 else (HEADLINE_MODELS if not wl_hidden(workload) else 148)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K_run,
             "warmup": W, "ms_per_step": med / K_run * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(workload, pack),
-            "timing": {"repeats": R, "window_ms": total * 1e3, "per_launch": "median of the repeats"},
+            "timing": {"repeats": R, "window_ms": total * 1e3, "method": "R x K steps in one call of the port"},
             "reference_probe": reference_probe(),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_models} of the pack's runs (one per host thread) x {K_run} steps x {R} "
@@ -294,28 +295,39 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
-def timed_repeats(ctx, launch, est_ms=None, min_window_ms=MIN_WINDOW_MS, max_repeats=4000):
+def timed_repeats(ctx, launch, est_ms=None, min_window_ms=MIN_WINDOW_MS, max_repeats=20000):
     """Repeats `launch()` (which enqueues one K-step unit of work on the current stream) back to back
     until the window is >= min_window_ms; CUDA events between launches.  Returns (median ms per launch
-    (max over ranks), window ms (max over ranks), repeats)."""
+    (max over ranks), window ms (max over ranks), repeats, kernels of libvae_b200 launched in the window)."""
+    from vae_training_b200 import _lib
     torch = ctx.torch
+    count = _lib.load().vae_launch_count
     if est_ms is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launch()                                  # first call may include one-time set-up
         e0.record()
         launch()
         e1.record()
         torch.cuda.synchronize()
         est_ms = max(e0.elapsed_time(e1), 1e-3)
-    R = int(min(max_repeats, max(3, math.ceil(min_window_ms / est_ms))))
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
-    ctx.barrier()
-    ev[0].record()
-    for i in range(R):
-        launch()
-        ev[i + 1].record()
-    ctx.barrier()
+    R = int(min(max_repeats, max(3, math.ceil(1.15 * min_window_ms / est_ms))))
+    while True:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+        ctx.barrier()
+        l0 = count()
+        ev[0].record()
+        for i in range(R):
+            launch()
+            ev[i + 1].record()
+        launches = count() - l0
+        ctx.barrier()
+        window = ctx.max_over_ranks(ev[0].elapsed_time(ev[R]))
+        short = ctx.max_over_ranks(1.0 if (window < min_window_ms and R < max_repeats) else 0.0)
+        if not short:
+            break
+        R = int(min(max_repeats, math.ceil(R * 1.3 * min_window_ms / max(window, 1e-3))))    # every rank agrees to go again
     d = [ev[i].elapsed_time(ev[i + 1]) for i in range(R)]
-    return ctx.max_over_ranks(float(np.median(d))), ctx.max_over_ranks(ev[0].elapsed_time(ev[R])), R
+    return ctx.max_over_ranks(float(np.median(d))), window, R, int(launches)
 
 
 def ffma_peak(ctx):
@@ -370,7 +382,7 @@ def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key):
 
 def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states=False):
     """Device-resident throughput of one homogeneous pack: W warm-up steps, then R x (K-step launch)."""
-    from vae_training_b200 import _lib, init
+    from vae_training_b200 import init
     from vae_training_b200.packed import PackedRuns
     torch = ctx.torch
     specs = make_specs(workload, n_models, first_index=first_index)
@@ -380,9 +392,7 @@ def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states
     runs.prepare()
     runs.train_steps(W)
     torch.cuda.synchronize()
-    l0 = _lib.load().vae_launch_count()
-    ms, window, R = timed_repeats(ctx, lambda: runs.train_steps(K))
-    launches = _lib.load().vae_launch_count() - l0
+    ms, window, R, launches = timed_repeats(ctx, lambda: runs.train_steps(K))
     loss_dev = runs.loss.view(n_models, runs.max_chunk)[:, :K]
     if not bool(torch.isfinite(loss_dev).all()):
         raise SystemExit(f"bench.py: non-finite loss in the timed region ({workload})")
@@ -440,7 +450,7 @@ def measure_sweep_mix(ctx, K, W, peak):
     launch(W)
     torch.cuda.synchronize()
     # a rank without runs (more ranks than runs) still takes part in the barriers / reductions
-    ms, window, R = timed_repeats(ctx, lambda: launch(K), est_ms=None if packs else MIN_WINDOW_MS)
+    ms, window, R, _ = timed_repeats(ctx, lambda: launch(K), est_ms=None if packs else MIN_WINDOW_MS)
     for r in packs:
         if not bool(torch.isfinite(r.loss.view(r.M, r.max_chunk)[:, :K]).all()):
             raise SystemExit("bench.py: non-finite loss in the sweep mix")
@@ -587,8 +597,10 @@ def run_b200(args):
             torch.cuda.synchronize()
             if not torch.equal(loss_snapshot, runs.loss.view(n_models, runs.max_chunk)[:, :K]):
                 raise SystemExit(f"bench.py: {mode} and the default launch disagree (must be bit-identical)")
-            ms_ab, _, _ = timed_repeats(ctx, lambda: runs.train_steps(K))
-            ab[mode] = total_models * K / (ms_ab * 1e-3)
+            ms_ab, _, _, _ = timed_repeats(ctx, lambda: runs.train_steps(K))
+            want_cluster = int(env["VAE_SMALL_CLUSTER"])
+            # a 2-CTA-cluster plan is only taken when it costs no residency (fused_small.cu:plan_small)
+            ab[mode] = total_models * K / (ms_ab * 1e-3) if (runs.plan.gm == 1 and runs.plan.cluster == want_cluster) else None
             for k in env:
                 del os.environ[k]
         runs.prepare()
@@ -603,7 +615,7 @@ def run_b200(args):
         return h2d, d2h
     h2d, d2h = e2e_unit()
     torch.cuda.synchronize()
-    ms_e2e, window_e2e, R_e2e = timed_repeats(ctx, e2e_unit)
+    ms_e2e, window_e2e, R_e2e, _ = timed_repeats(ctx, e2e_unit)
     e2e_value = total_models * K / (ms_e2e * 1e-3)
     hl = runs.hloss[:n_models * K].numpy()
     if not np.isfinite(hl).all():

@@ -630,7 +630,10 @@ size_t mlp_job_bytes() { return sizeof(MlpJobDev); }
 
 // Function attributes are only ever set to the same constants (see fused_small.cu:set_kernel_attrs).
 static int mlp_set_attrs() {
-  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  cudaFuncAttributes fa;
+  VAE_CUDA_OK(cudaFuncGetAttributes(&fa, fused_mlp_kernel));       // the kernel also has static shared memory
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024 - (int)fa.sharedSizeBytes));
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   return 0;
 }
