@@ -221,7 +221,7 @@ typedef struct VaePackPlan {
   int32_t shape_id;       /* class 1: kernel instance                               */
   int32_t homogeneous;    /* class 1: every job has the same shape and batch        */
   int32_t gm;             /* class 1: models per CTA                                */
-  int32_t cluster;        /* CTAs per thread-block cluster                          */
+  int32_t cluster;        /* CTAs per thread-block cluster (class 2: 0 = tensor-core kernel, one CTA per model) */
   int32_t nbuf;           /* class 1: eps buffers (2 = drawn one step ahead)        */
   uint64_t smem_bytes;    /* dynamic shared memory per CTA                          */
   void* d_jobs;           /* device job table (= d_scratch)                         */
@@ -262,6 +262,17 @@ int64_t vae_launch_count(void);
  * float[>= blocks*threads]; *flops_out = total flops issued. */
 int vae_ffma_probe(float* d_sink, int32_t blocks, int32_t threads, int32_t iters,
                    double* flops_out, void* stream);
+
+/* tcgen05 operand-form probe (hardware self-check, not on the training path): copies two caller-built
+ * shared-memory operand images verbatim, issues `ksteps` M128 x N x K8 kind::tf32 MMAs with the given
+ * descriptor high words (everything except the start address; a_step / b_step bytes are added to the start
+ * addresses per k-step; the k loop runs `repeat` times) and instruction descriptor, and returns the 128 x N
+ * FP32 accumulator in d_out[0 .. 128 N) and the elapsed SM cycles (first issue -> completion) in d_out[128 N].
+ * Documents what fused_mlp_tc.cu assumes about K-/MN-major SWIZZLE_128B descriptors, N = 104 and the
+ * truncation of raw FP32 operands to TF32. */
+int vae_umma_probe(const float* d_a_img, int32_t a_bytes, const float* d_b_img, int32_t b_bytes,
+                   uint64_t desc_a_hi, uint64_t desc_b_hi, uint32_t idesc, int32_t ksteps, int32_t a_step,
+                   int32_t b_step, int32_t N, int32_t repeat, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

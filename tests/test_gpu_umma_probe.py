@@ -1,0 +1,103 @@
+"""Hardware self-check of the tcgen05 operand forms fused_mlp_tc.cu relies on (vae_umma_probe): K-major and
+MN-major SWIZZLE_128B shared-memory descriptors for kind::tf32, N = 104, and the handling of the low 13
+mantissa bits of raw FP32 operands.  The images are built here in NumPy with the layout formula the kernel
+uses (canonical UMMA SWIZZLE_128B: 128-byte rows, 16-byte chunk index XOR (row % 8), 8-row groups of 1024 B)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def sw128_image(mat):
+    """mat[rows][cols] (rows % 8 == 0, cols % 32 == 0) -> float32 image: for each 32-column atom a block of
+    rows x 128 B; element (r, c): chunk = (c % 32) // 4 stored at chunk ^ (r % 8)."""
+    rows, cols = mat.shape
+    assert rows % 8 == 0 and cols % 32 == 0
+    img = np.zeros((cols // 32, rows, 32), np.float32)
+    for a in range(cols // 32):
+        blk = mat[:, 32 * a:32 * a + 32].reshape(rows, 8, 4)
+        for r in range(rows):
+            perm = np.arange(8) ^ (r % 8)
+            img[a, r].reshape(8, 4)[perm] = blk[r]
+    return img.reshape(-1)
+
+
+def desc_hi(lbo_bytes, sbo_bytes):
+    return ((lbo_bytes >> 4) << 16) | ((sbo_bytes >> 4) << 32) | (1 << 46) | (2 << 61)
+
+
+def idesc(n, a_mn=False, b_mn=False):
+    return (1 << 4) | (2 << 7) | (2 << 10) | (int(a_mn) << 15) | (int(b_mn) << 16) | ((n >> 3) << 17) | ((128 >> 4) << 24)
+
+
+def trunc_tf32(x):
+    return (np.asarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def rna_tf32(x):
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def run(lib, a_img, b_img, da, db, idesc_, ksteps, a_step, b_step, n, repeat=1, cycles=False):
+    ta, tb = torch.from_numpy(a_img).cuda(), torch.from_numpy(b_img).cuda()
+    out = torch.zeros(128 * n + 8, device="cuda")
+    rc = lib.load().vae_umma_probe(C.c_void_p(ta.data_ptr()), a_img.nbytes, C.c_void_p(tb.data_ptr()), b_img.nbytes,
+                                   C.c_uint64(da), C.c_uint64(db), C.c_uint32(idesc_), ksteps, a_step, b_step, n, repeat,
+                                   C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    lib.check(rc, "vae_umma_probe")
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    return float(res[128 * n]) if cycles else res[:128 * n].reshape(128, n)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vae_training_b200 import _lib
+    return _lib
+
+
+def relerr(got, ref):
+    return float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+
+
+def test_kmajor_operands_and_raw_fp32_truncation(lib):
+    """Both operands K-major, N = 104, K = 32: also decides how raw FP32 operands are narrowed to TF32."""
+    rng = np.random.default_rng(0)
+    n = 104
+    A = rng.standard_normal((128, 32)).astype(np.float32)
+    B = rng.standard_normal((n, 32)).astype(np.float32)
+    got = run(lib, sw128_image(A), sw128_image(B), desc_hi(16, 1024), desc_hi(16, 1024), idesc(n), 4, 32, 32, n)
+    ref_t = trunc_tf32(A).astype(np.float64) @ trunc_tf32(B).astype(np.float64).T
+    ref_r = rna_tf32(A).astype(np.float64) @ rna_tf32(B).astype(np.float64).T
+    et, er = relerr(got, ref_t), relerr(got, ref_r)
+    print(f"raw fp32 operands: error vs truncation model {et:.2e}, vs round-to-nearest model {er:.2e}")
+    assert et <= 2e-6, (et, er)           # the tensor core ignores the low 13 mantissa bits
+    assert er > 20 * et
+
+
+def test_mn_major_a_and_b(lib):
+    """The dW form: A = X^T and B = dY^T, both read MN-major from batch-major images (rows = batch = K)."""
+    rng = np.random.default_rng(1)
+    kb, n = 24, 104                                                     # 3 k-steps of 8 batch rows
+    X = trunc_tf32(rng.standard_normal((kb, 128)).astype(np.float32))   # [b][k_feature] : M = 128 features
+    dY = trunc_tf32(rng.standard_normal((kb, 128)).astype(np.float32))  # [b][n_feature] : N = 104 of 128 stored
+    got = run(lib, sw128_image(X), sw128_image(dY), desc_hi(kb * 128, 1024), desc_hi(kb * 128, 1024),
+              idesc(n, a_mn=True, b_mn=True), kb // 8, 1024, 1024, n)
+    ref = X.astype(np.float64).T @ dY.astype(np.float64)[:, :n]
+    assert relerr(got, ref) <= 2e-6
+
+
+def test_kmajor_a_mn_major_b(lib):
+    """The forward form with W stored (in, out): A = activations K-major, B = W read MN-major (rows = k)."""
+    rng = np.random.default_rng(2)
+    k, n = 32, 104
+    A = trunc_tf32(rng.standard_normal((128, k)).astype(np.float32))
+    W = trunc_tf32(rng.standard_normal((k, 128)).astype(np.float32))    # [k][n], 104 of 128 columns used
+    got = run(lib, sw128_image(A), sw128_image(W), desc_hi(16, 1024), desc_hi(k * 128, 1024), idesc(n, b_mn=True),
+              4, 32, 1024, n)
+    ref = A.astype(np.float64) @ W.astype(np.float64)[:, :n]
+    assert relerr(got, ref) <= 2e-6

@@ -86,6 +86,8 @@ _PROTOTYPES = {
     "vae_transpose_split_tf32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "vae_gemm_nt_3xtf32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_int64, _P,
                                      C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
+    "vae_umma_probe": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vae_last_error": (C.c_char_p, []),
     "vae_abi_version": (C.c_int, []),
     "vae_launch_count": (C.c_int64, []),

@@ -20,6 +20,19 @@ size_t mlp_job_bytes();
 int mlp_prepare(int n_jobs, size_t smem, size_t smem4, VaePackPlan* plan);
 int mlp_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
 int mlp_resident_jobs(size_t smem, size_t smem4, int* out);
+// fused_mlp_tc.cu (tensor-core kernel for the same class-2 jobs; one CTA per model)
+int mlp_tc_supported(const VaeTrainJob* j, size_t* ws_bytes);
+size_t mlp_tc_job_bytes();
+int mlp_tc_fill_job(const VaeTrainJob& j, void* out);
+int mlp_tc_prepare();
+int mlp_tc_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
+
+// VAE_MLP_TC=0 keeps hidden-layer models on the FP32 FFMA cluster kernel (A/B runs, bit-identity tests)
+static bool use_mlp_tc(const VaeTrainJob* j, size_t* ws) {
+  const char* e = getenv("VAE_MLP_TC");
+  if (!e || e[0] != '1') return false;          // opt-in while the tensor-core kernel is being brought up
+  return mlp_tc_supported(j, ws) != 0;
+}
 }  // namespace vae
 
 extern "C" {
@@ -31,8 +44,11 @@ int vae_train_fused_supported(const VaeTrainJob* job) {
 }
 
 size_t vae_train_fused_workspace_bytes(const VaeTrainJob* job) {
-  size_t ws = 0;
-  if (job && !vae::small_supported(job) && vae::mlp_supported(job, nullptr, &ws)) return ws;
+  size_t ws = 0, wt = 0;
+  if (job && !vae::small_supported(job) && vae::mlp_supported(job, nullptr, &ws)) {
+    if (vae::mlp_tc_supported(job, &wt) && wt > ws) ws = wt;      // either kernel may be chosen when the pack is prepared
+    return ws;
+  }
   return 0;
 }
 
@@ -54,13 +70,20 @@ int vae_train_fused_resident_jobs(const VaeTrainJob* job) {
   }
   size_t smem = 0, smem4 = 0;
   if (!vae::mlp_supported(job, &smem, nullptr, &smem4)) return 0;
+  if (vae::use_mlp_tc(job, nullptr)) {                              // tensor-core kernel: one CTA (= model) per SM
+    int dev = 0, sms = 0;
+    VAE_CUDA_OK(cudaGetDevice(&dev));
+    VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return sms;
+  }
   int out = 0;
   const int rc = vae::mlp_resident_jobs(smem, smem4, &out);
   return rc ? rc : out;
 }
 
 size_t vae_train_fused_scratch_bytes(int32_t n_jobs) {
-  const size_t per = vae::small_job_bytes() > vae::mlp_job_bytes() ? vae::small_job_bytes() : vae::mlp_job_bytes();
+  size_t per = vae::small_job_bytes() > vae::mlp_job_bytes() ? vae::small_job_bytes() : vae::mlp_job_bytes();
+  if (vae::mlp_tc_job_bytes() > per) per = vae::mlp_tc_job_bytes();
   return n_jobs > 0 ? (size_t)n_jobs * per : 0;
 }
 
@@ -87,6 +110,34 @@ int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, s
   if (cls == 1) {
     if ((rc = vae::small_prepare(jobs, n_jobs, d_scratch, s, plan))) return rc;
   } else {
+    // class 2 on the tensor cores: one CTA per model (every job must qualify, else the FFMA cluster kernel runs the pack)
+    bool tc = true;
+    for (int i = 0; i < n_jobs && tc; ++i) tc = vae::use_mlp_tc(&jobs[i], nullptr);
+    if (tc) {
+      const size_t tjb = vae::mlp_tc_job_bytes();
+      char* th = (char*)malloc((size_t)n_jobs * tjb);
+      VAE_REQUIRE(th, "vae_pack_prepare: out of host memory");
+      for (int i = 0; i < n_jobs; ++i) {
+        const VaeTrainJob& j = jobs[i];
+        if (!j.params || !j.adam_m || !j.adam_v || !j.step || !j.model_key || !j.dataset_key || !j.loss_out ||
+            !j.workspace || (j.data.kind != VAE_DATA_SPHERE && !j.A)) {
+          free(th);
+          vae::set_error("vae_pack_prepare: job %d has a NULL device pointer (class 2 needs a zero-filled workspace of "
+                         "vae_train_fused_workspace_bytes() bytes)", i);
+          return VAE_ERR_INVALID;
+        }
+        rc = vae::mlp_tc_fill_job(j, th + (size_t)i * tjb);
+        if (rc) { free(th); return rc; }
+      }
+      cudaError_t e = cudaMemcpyAsync(d_scratch, th, (size_t)n_jobs * tjb, cudaMemcpyHostToDevice, s);
+      free(th);
+      VAE_CUDA_OK(e);
+      if ((rc = vae::mlp_tc_prepare())) return rc;
+      plan->cls = 2; plan->n_jobs = n_jobs; plan->d_jobs = d_scratch; plan->cluster = 0; plan->smem_bytes = 0;
+      plan->abi = VAE_B200_ABI_VERSION;
+      plan->device = dev;
+      return 0;
+    }
     // class 2: one cluster per model
     const size_t jb = vae::mlp_job_bytes();
     char* host = (char*)malloc((size_t)n_jobs * jb);
@@ -125,6 +176,7 @@ int vae_pack_train(const VaePackPlan* plan, int64_t n_steps, void* stream) {
               "vae_pack_train: plan was not produced by vae_pack_prepare of this library version");
   if (n_steps == 0) return 0;
   if (plan->cls == 1) return vae::small_launch(plan, n_steps, (cudaStream_t)stream);
+  if (plan->cls == 2 && plan->cluster == 0) return vae::mlp_tc_launch(plan, n_steps, (cudaStream_t)stream);
   if (plan->cls == 2) return vae::mlp_launch(plan, n_steps, (cudaStream_t)stream);
   vae::set_error("vae_pack_train: bad plan class %d", plan->cls);
   return VAE_ERR_INVALID;

@@ -1,0 +1,929 @@
+// fused_mlp_tc.cu -- persistent fused training loop for the hidden-layer VAEs of the sphere sweep
+// (sphere_vae_padding_expts.sh: enc = dec = 200|200|200) on the 5th-generation tensor cores: ONE CTA per
+// model, every Dense layer of the step (forward, dX, dW) is a tcgen05.mma.kind::tf32 GEMM with the whole
+// batch as one M = 128 tile and the accumulator in tensor memory.
+//
+// The hot-loop body is the one fused_mlp.cu implements with FP32 FFMA on a thread-block cluster
+// (model.py:221-222: key splits, eps draw, dataset batch, VAE.apply networks.py:61-84, sampled ELBO :94-98,
+// hand-derived backward, legacy flax Adam vae.py:113).  Here a model's step is a chain of 23 GEMMs
+//     forward   Y[b][n]  = act(X[b][:] . WT[n][:] + bias[n])          A = X  (batch-major),   B = W^T
+//     dX        dX[b][k] = (dY[b][:] . W[k][:]) * relu'(X[b][k])      A = dY (batch-major),   B = W
+//     dW        dW[k][n] = XT[k][:] . dYT[n][:]   (+ Adam epilogue)    A = X^T (feature-major), B = dY^T
+// -- all "NT" (both operands K-contiguous).  tcgen05 reads kind::tf32 operands K-major from shared memory
+// (MN-major TF32 operands would need the SWIZZLE_128B_BASE32B layout, see umma_probe.cu), so every
+// activation / gradient is kept in two global (L2-resident) copies, batch-major and feature-major [f][b],
+// written by the producing GEMM's epilogue straight from tensor memory; weights are kept as W (the Adam master
+// copy) and W^T [n][k] (rewritten by the Adam epilogue).
+// Global layouts follow the tensor-memory drain pattern (thread = accumulator row, 8 consecutive columns per
+// tcgen05.ld): a "row-per-thread" matrix X[r][c] is stored GROUP-MAJOR, [c / 8][r][8], so the 32 lanes of a
+// warp write 32 x 32 contiguous bytes (one 256-bit store each) instead of 32 strided sectors; the operand
+// stager reads the same arrays as 16-byte pieces.  This holds for the batch-major activations / gradients
+// (r = batch row) and for W, m, v (r = k, the dW accumulator row).  Feature-major copies and W^T are plain
+// row-major (their stores are lane-contiguous already).
+//
+// FP32-level accuracy from TF32 tensor cores: every operand is split x = hi + lo with hi = TF32(x) rounded to
+// nearest and lo = x - hi (exact in FP32, |lo| <= 2^-11 |x|; the tensor core ignores the low 13 mantissa bits
+// of what it is given -- measured, tests/test_gpu_umma_probe.py -- so hi is used exactly and lo to 2^-22 |x|);
+// a product is accumulated as
+//     A.B ~= Ah.Bh + Ah.Bl + Al.Bh        (three MMAs per K = 8 step; the dropped Al.Bl term is ~2^-22 relative
+//                                          per element with either sign)
+// Only algorithmic flops (2MNK) are ever reported as useful work.
+//
+// Pipeline per GEMM: K is walked in chunks of 16 through a 3-stage shared-memory ring.  All 256 threads
+// stage a chunk: 16-byte cp.async copies from the row-major global operands into the canonical K-major
+// no-swizzle core-matrix layout (8 rows x 16 bytes, contiguous 128 bytes; LBO = 128 B between K chunks,
+// SBO = 512 B between 8-row groups) = the hi operand; each thread then derives the lo pieces of what it
+// copied; one thread issues the chunk's MMAs and a tcgen05.commit that frees the ring slot.  After the last
+// chunk the accumulator (128 lanes x N columns per M tile) is drained with tcgen05.ld by all 8 warps (lane
+// quarter = warp % 4, column groups split between the two warps of a quarter) into the fused epilogue:
+// bias + relu, relu mask, reparameterisation, loss partials, or Adam.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vae {
+
+constexpr int kTT = 256;                        // threads per CTA
+constexpr int kTKC = 16;                        // K elements per staged chunk (two K = 8 MMA steps)
+constexpr int kTMaxStages = 6;
+constexpr int kTMaxN = 208;                     // most B rows (accumulator columns) of one GEMM
+constexpr int kTATile = 128 * kTKC * 4;         // one M tile of A (hi or lo) per stage: 8 KB
+constexpr int kTRingBytes = 176 * 1024;         // the operand ring; a GEMM cuts it into stages of its own size
+constexpr int kTSmemBytes = kTRingBytes + 1024;
+constexpr int kTMaxL = VAE_MAX_HIDDEN + 1;
+
+__host__ __device__ constexpr int t_up8(int n) { return (n + 7) & ~7; }
+__host__ __device__ constexpr int t_up4(int n) { return (n + 3) & ~3; }
+
+// One Dense layer K -> N.  Offsets are in floats from the model's workspace base.
+struct TcLayer {
+  int32_t K, N, Kp, Np;            // logical sizes, padded to multiples of 8
+  int32_t Kuse;                    // input rows that can be non-zero (encoder layer 0: DR, the non-padding columns)
+  int32_t flat_w, flat_b;          // offsets in the flat parameter vector (include/vae_b200.h)
+  int32_t W, Bv, WT;               // W [K][Np] (Adam master), bias [Np], WT [Np][Kp]; adam m / v at + pm_stride / 2 pm_stride
+  int32_t in_bm, in_T;             // layer input: batch-major [BP][Kp], feature-major [Kp + 8][BP] (row Kuse = ones)
+  int32_t out_bm, out_T;           // layer output (hidden layers): batch-major [BP][Np], feature-major [Np + 8][BP]
+  int32_t in_mask, out_mask;       // relu masks (output > 0) of the input / output activation: [BP][32] bytes, one per 8 columns
+};
+
+struct TcJobDev {
+  float* params; float* adam_m; float* adam_v; int32_t* step;
+  uint32_t* model_key; uint32_t* dataset_key; const float* A; float* loss_out; float* ws;
+  int32_t B, BP, D, L, DR, kind, G, dd, tunable, n_enc, n_dec;
+  int32_t Lp, Dp, LD;
+  int32_t off_lv, off_eps;         // flat offsets of epsilon_p, epsilon
+  int32_t pm_stride;               // floats between the aligned P, M and V parameter regions
+  int32_t ws_z, ws_gn, ws_mu, ws_gbm[2], ws_gT[2];
+  int32_t n_flat;
+  TcLayer enc[kTMaxL], dec[kTMaxL];
+  float eps0, lr, b1, b2, omb1, omb2, adam_eps;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem(bar)), "r"(count));
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = t_smem(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void t_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void t_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: LBO = 128 B (next 16-byte K chunk), SBO = 512 B (next 8-row group), version 1
+__device__ __forceinline__ uint64_t t_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+}
+// c = F32, a = b = TF32, both K-major, N >> 3 at [17,23), M = 128 (>> 4) at [24,29)
+__device__ __forceinline__ uint32_t t_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void t_cp16(uint32_t dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void t_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 8 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void t_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+// main + correction accumulator columns (single-tile GEMMs, see tc_gemm)
+__device__ __forceinline__ void t_ld8_sum(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8], c[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]) : "r"(taddr + 256u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(c[j]);
+}
+__device__ __forceinline__ void t_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// TF32(x), round to nearest (ties away): the tensor core would TRUNCATE a raw FP32 operand, which biases every
+// product the same way; with hi rounded, lo = x - hi (exact in FP32) has either sign
+__device__ __forceinline__ float t_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// 256-bit global accesses (LDG/STG.E.256): one full 32-byte sector per lane
+__device__ __forceinline__ void t_ldg8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void t_stg8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ float t_sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+struct TcHyper { float lr, b1, b2, omb1, omb2, eps, ibc1, ibc2; };
+__device__ __forceinline__ float t_adam(float p, float& m, float& v, float g, const TcHyper& h) {
+  m = h.b1 * m + h.omb1 * g;
+  v = h.b2 * v + h.omb2 * g * g;
+  return p - __fdividef(h.lr * (m * h.ibc1), t_sqrt_approx(v * h.ibc2) + h.eps);
+}
+
+#ifdef VAE_TC_PROFILE
+__device__ long long g_tc_prof[16];
+#define TC_T0() const long long _t0 = clock64()
+#define TC_ACC(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_prof[i] += clock64() - _t0; } while (0)
+#else
+#define TC_T0() do {} while (0)
+#define TC_ACC(i) do {} while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------ GEMM main loop
+struct TcRing {
+  uint8_t* base;                  // kTRingBytes, 1024-byte aligned
+  uint64_t* empty;                // [kTMaxStages] ring slot free (tcgen05.commit of the MMAs that read it)
+  uint64_t* accfull;              // accumulator complete
+  float* bias_s;                  // [kTMaxN] bias of the running GEMM (forward epilogues)
+  uint32_t par;                   // bit s: parity of empty[s]'s next completion
+  uint32_t pend;                  // bit s: a commit on empty[s] has not been waited for yet
+  uint32_t gemms;                 // GEMMs finished so far
+  uint32_t tmem;                  // tensor-memory base (M tile t accumulates at column 256 t)
+};
+
+template <int N>
+__device__ __forceinline__ void t_cp_wait_dyn(int n) {
+  if (n >= N) t_cp_wait<N>();
+  else if constexpr (N > 0) t_cp_wait_dyn<N - 1>(n);
+}
+
+// A GEMM operand in global memory: rows x K floats.
+//   grouped = 0: row-major, element (r, k) at ptr[r * ld + k]                      (ld = row stride, a multiple of 4)
+//   grouped = 1: group-major [k / 8][r][8], element (r, k) at ptr[((k >> 3) * ld + r) * 8 + (k & 7)]   (ld = rows per group block)
+struct TcOperand { const float* ptr; int ld; int grouped; };
+__device__ __forceinline__ const float* tc_piece(const TcOperand& o, int r, int k) {      // k a multiple of 4
+  return o.grouped ? o.ptr + ((size_t)(k >> 3) * o.ld + r) * 8 + (k & 7) : o.ptr + (size_t)r * o.ld + k;
+}
+
+// D[m][n] = sum_k A[m][k] B[n][k]:  A rows [0, a_rows) (M tiles of 128), B rows [0, b_rows), k < kpad (multiple of 8).
+// n_mma (multiple of 8, >= b_rows): MMA N.  bias (may be null): n_bias floats copied to R.bias_s while the main loop runs.
+// The ring is cut into stages of this GEMM's own size, (128 m_tiles + up8(b_rows)) x 16 floats x {hi, lo}: 4 stages
+// for the single-tile GEMMs, 3 for the two-tile dW; chunk c + stages - 1 is in flight while chunk c is multiplied.
+// Thread -> piece mapping: consecutive lanes take the 8 rows of a core matrix (16 bytes apart in shared memory: a
+// quarter warp covers all 32 banks), then the next 16-byte K piece.
+// On return the accumulator is complete and visible to tcgen05.ld (all threads have waited).
+__device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int a_rows, int m_tiles,
+                                        const TcOperand Bm, int b_rows, int n_mma, int kpad,
+                                        const float* __restrict__ bias = nullptr, int n_bias = 0) {
+  const int tid = threadIdx.x;
+  const int nchunk = (kpad + kTKC - 1) / kTKC;
+  const uint32_t idesc = t_idesc(n_mma);
+  const int a_groups = (a_rows + 7) >> 3, n_pieces = (a_groups + ((b_rows + 7) >> 3)) * 32;     // 8 rows x 4 K pieces per group
+  const int a_bytes = m_tiles * kTATile, b_bytes = t_up8(b_rows) * kTKC * 4;
+  const int stage_bytes = 2 * (a_bytes + b_bytes);
+  int nstages = kTRingBytes / stage_bytes;
+  nstages = nstages > kTMaxStages ? kTMaxStages : nstages;
+  const int ahead = nstages - 1;                   // chunks in flight beyond the one being multiplied
+
+  auto issue_loads = [&](int c) {
+    const int stage = c % nstages;
+    if (R.pend & (1u << stage)) {                  // the MMAs that read this slot have retired
+      t_mbar_wait(&R.empty[stage], (R.par >> stage) & 1u);
+      R.par ^= 1u << stage; R.pend &= ~(1u << stage);
+    }
+    const int k0 = c * kTKC;
+    const int kw4 = min(kTKC, kpad - k0) >> 2;                         // 16-byte pieces per row in this chunk (2 or 4)
+    const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + 2 * a_bytes;
+    for (int p = tid; p < n_pieces; p += kTT) {
+      const int grp = p >> 5, pc = (p >> 3) & 3, r8 = p & 7;
+      if (pc >= kw4) continue;
+      if (grp < a_groups) {
+        const int row = grp * 8 + r8;
+        if (row < a_rows) t_cp16(sA + (uint32_t)((grp * 4 + pc) * 128 + r8 * 16), tc_piece(A, row, k0 + 4 * pc));
+      } else {
+        const int gb = grp - a_groups, row = gb * 8 + r8;
+        if (row < b_rows) t_cp16(sB + (uint32_t)((gb * 4 + pc) * 128 + r8 * 16), tc_piece(Bm, row, k0 + 4 * pc));
+      }
+    }
+  };
+  // hi = TF32(x) (in place), lo = x - hi, of exactly the pieces this thread copied (its own cp.async groups are complete)
+  auto make_lo = [&](int c) {
+    const int stage = c % nstages;
+    const int k0 = c * kTKC;
+    const int kw4 = min(kTKC, kpad - k0) >> 2;
+    uint8_t* sA = R.base + (size_t)stage * stage_bytes;
+    uint8_t* sB = sA + 2 * a_bytes;
+    for (int p = tid; p < n_pieces; p += kTT) {
+      const int grp = p >> 5, pc = (p >> 3) & 3, r8 = p & 7;
+      if (pc >= kw4) continue;
+      uint8_t* hi; uint8_t* lo;
+      if (grp < a_groups) {
+        if (grp * 8 + r8 >= a_rows) continue;
+        hi = sA + (grp * 4 + pc) * 128 + r8 * 16; lo = hi + a_bytes;
+      } else {
+        const int gb = grp - a_groups;
+        if (gb * 8 + r8 >= b_rows) continue;
+        hi = sB + (gb * 4 + pc) * 128 + r8 * 16; lo = hi + b_bytes;
+      }
+      const float4 x = *reinterpret_cast<const float4*>(hi);
+      const float4 h = make_float4(t_hi(x.x), t_hi(x.y), t_hi(x.z), t_hi(x.w));
+      *reinterpret_cast<float4*>(hi) = h;
+      *reinterpret_cast<float4*>(lo) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+    }
+  };
+
+  TC_T0();
+  for (int c = 0; c < ahead; ++c) {                // prologue: `ahead` groups (empty ones past the end keep the count uniform)
+    if (c < nchunk) issue_loads(c);
+    t_cp_commit();
+  }
+  if (bias != nullptr)
+    for (int i = tid; i < n_bias; i += kTT) R.bias_s[i] = bias[i];    // visible after the main loop's barriers
+  for (int c = 0; c < nchunk; ++c) {
+    t_cp_wait_dyn<kTMaxStages - 2>(ahead - 1);     // all but the newest ahead - 1 groups are complete: chunk c has landed
+#if !defined(VAE_TC_EXP) || VAE_TC_EXP != 1
+    make_lo(c);
+#endif
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> tensor-core reads
+    __syncthreads();
+    const int stage = c % nstages;
+    if (tid == 0) {
+      t_fence_after();
+      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + 2 * a_bytes;
+      const int ksteps = min(kTKC, kpad - c * kTKC) >> 3;
+      for (int s = 0; s < ksteps; ++s) {
+        const uint64_t dBh = t_desc(sB + s * 256), dBl = t_desc(sB + b_bytes + s * 256);
+        for (int t = 0; t < m_tiles; ++t) {
+          const uint64_t dAh = t_desc(sA + t * kTATile + s * 256), dAl = t_desc(sA + a_bytes + t * kTATile + s * 256);
+          const uint32_t d = R.tmem + (uint32_t)(t * 256);
+          // The tensor core accumulates FP32 with round-toward-zero.  Single-tile GEMMs (forward, dX: K up to 200)
+          // keep the two correction products in their own accumulator (columns 256..) so that the small terms are
+          // never truncated against the large main sum and the main chain is a third as long; the epilogue adds
+          // the two.  Two-tile GEMMs (dW, K = batch) have no columns to spare and a chain of only 39 MMAs.
+          const uint32_t dc = m_tiles == 1 ? d + 256u : d;
+          t_mma(d, dAh, dBh, idesc, (c | s) != 0);
+          t_mma(dc, dAh, dBl, idesc, m_tiles == 1 ? (uint32_t)((c | s) != 0) : 1u);
+          t_mma(dc, dAl, dBh, idesc, 1u);
+        }
+      }
+      t_commit(&R.empty[stage]);
+      if (c == nchunk - 1) t_commit(R.accfull);
+    }
+    R.pend |= 1u << stage;
+    // refill the slot chunk c - 1 was multiplied from (its MMAs were queued one iteration ago) while chunk c runs
+#if defined(VAE_TC_EXP) && VAE_TC_EXP == 2
+    if (c + ahead < nchunk && R.pend & (1u << ((c + ahead) % nstages))) {
+      const int st = (c + ahead) % nstages;
+      t_mbar_wait(&R.empty[st], (R.par >> st) & 1u); R.par ^= 1u << st; R.pend &= ~(1u << st);
+    }
+#else
+    if (c + ahead < nchunk) issue_loads(c + ahead);
+#endif
+    t_cp_commit();
+  }
+  TC_ACC(0);
+  t_mbar_wait(R.accfull, R.gemms & 1u);
+  TC_ACC(1);
+  R.gemms += 1;
+  R.par ^= R.pend; R.pend = 0;                     // every outstanding commit has completed with the accumulator
+  t_fence_after();
+}
+
+// End of an epilogue: TMEM reads and global writes of all threads are done before the next GEMM starts.
+__device__ __forceinline__ void tc_epilogue_done() {
+  t_fence_before();
+  __syncthreads();
+}
+
+__device__ __forceinline__ float tc_block_sum(float v, float* red) {   // result valid in every thread
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kTT / 32; ++i) t += red[i];
+  return t;
+}
+
+// Element (k, n) of a layer's group-major W / m / v copy (see the header): [n / 8][k][8]
+__device__ __forceinline__ size_t tc_w8(const TcLayer& Ly, int k, int n) { return ((size_t)(n >> 3) * Ly.K + k) * 8 + (n & 7); }
+
+// Adam epilogue of dW in the NORMAL orientation: accumulator row = k (M tile t, lane r -> k = 128 t + r), column = n.
+// Row Kuse is the bias (the ones row of X^T).  Updates W / m / v (group-major: one 256-bit access per lane and column
+// group, lanes contiguous) and W^T.  The parameter / moment loads of the next two column groups are in flight while a
+// group is updated (the state lives in L2 / HBM).
+struct TcPmv { float p[8], m[8], v[8]; };
+__device__ __forceinline__ void tc_pmv_load(const float* P, int pm, TcPmv& x) {
+  t_ldg8(P, x.p); t_ldg8(P + pm, x.m); t_ldg8(P + 2 * pm, x.v);
+}
+__device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
+                                               const TcHyper& hp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, half = warp >> 2;
+  const int ngroups = Ly.Np >> 3;
+  for (int t = 0; t < m_tiles; ++t) {
+    if (t * 128 + q * 32 > Ly.Kuse) continue;                        // no row of this warp's lane quarter is a parameter
+    const int k = t * 128 + q * 32 + lane;
+    const bool is_w = k < Ly.Kuse, is_b = k == Ly.Kuse, live = is_w || is_b;
+    // address of column group g: kernel row k -> W + (g K + k) 8 ; bias -> Bv + 8 g
+    const float* base = is_b ? ws + Ly.Bv : ws + Ly.W + (size_t)(live ? k : 0) * 8;
+    const size_t gstride = is_b ? 8 : (size_t)Ly.K * 8;
+    TcPmv buf[3];
+    if (live) {
+      if (half < ngroups) tc_pmv_load(base + half * gstride, pm, buf[0]);
+      if (half + 2 < ngroups) tc_pmv_load(base + (half + 2) * gstride, pm, buf[1]);
+    }
+    int slot = 0;
+    for (int g = half; g < ngroups; g += 2, slot = slot == 2 ? 0 : slot + 1) {
+      const int pre = slot == 0 ? 2 : slot - 1;                       // slot that becomes free: prefetch group g + 4 into it
+      if (live && g + 4 < ngroups) {
+        const float* pp = base + (g + 4) * gstride;
+        if (pre == 0) tc_pmv_load(pp, pm, buf[0]);
+        else if (pre == 1) tc_pmv_load(pp, pm, buf[1]);
+        else tc_pmv_load(pp, pm, buf[2]);
+      }
+      float acc[8];
+      if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
+      else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
+      if (!live) continue;
+      TcPmv x = slot == 0 ? buf[0] : slot == 1 ? buf[1] : buf[2];
+      const int n0 = g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n0 + j < Ly.N) x.p[j] = t_adam(x.p[j], x.m[j], x.v[j], acc[j], hp);
+      float* P = const_cast<float*>(base) + g * gstride;
+      t_stg8(P, x.p); t_stg8(P + pm, x.m); t_stg8(P + 2 * pm, x.v);
+      if (is_w) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < Ly.N) ws[Ly.WT + (size_t)(n0 + j) * Ly.Kp + k] = x.p[j];
+      }
+    }
+  }
+}
+
+// Adam epilogue of dW in the TRANSPOSED orientation: accumulator row = n (tile t, lane r), column = k; column Kuse = bias.
+__device__ __forceinline__ void tc_adam_transposed(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
+                                                   int n_cols, const TcHyper& hp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, half = warp >> 2;
+  const int ngroups = n_cols >> 3;
+  for (int t = 0; t < m_tiles; ++t) {
+    const int n = t * 128 + q * 32 + lane;
+    for (int g = half; g < ngroups; g += 2) {
+      float acc[8];
+      if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
+      else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
+      if (n >= Ly.N) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = g * 8 + j;
+        if (k > Ly.Kuse) continue;
+        float* P = k == Ly.Kuse ? ws + Ly.Bv + n : ws + Ly.W + tc_w8(Ly, k, n);
+        float m = P[pm], v = P[2 * pm];
+        const float pn = t_adam(P[0], m, v, acc[j], hp);
+        P[0] = pn; P[pm] = m; P[2 * pm] = v;
+        if (k < Ly.Kuse) ws[Ly.WT + (size_t)n * Ly.Kp + k] = pn;
+      }
+    }
+  }
+}
+
+// dW of one layer (+ Adam).  Orientation: rows = the larger of (Kuse + 1, N) so the small dimension is the MMA N.
+__device__ __forceinline__ void tc_dw(TcRing& R, float* __restrict__ ws, const TcLayer& Ly, const float* gT, int BP, int pm,
+                                      const TcHyper& hp) {
+  const float* XT = ws + Ly.in_T;
+  if (Ly.Kuse + 1 >= Ly.N) {                       // normal: D[k][n]
+    const int rows = Ly.Kuse + 1, tiles = (rows + 127) >> 7;
+    tc_gemm(R, TcOperand{XT, BP, 0}, rows, tiles, TcOperand{gT, BP, 0}, Ly.N, Ly.Np, BP);
+    TC_T0();
+    tc_adam_normal(R, ws, Ly, pm, tiles, hp);
+    TC_ACC(2);
+  } else {                                          // transposed: D[n][k]
+    const int cols = t_up8(Ly.Kuse + 1), tiles = (Ly.N + 127) >> 7;
+    tc_gemm(R, TcOperand{gT, BP, 0}, Ly.N, tiles, TcOperand{XT, BP, 0}, Ly.Kuse + 1, cols, BP);
+    TC_T0();
+    tc_adam_transposed(R, ws, Ly, pm, tiles, cols, hp);
+    TC_ACC(3);
+  }
+  tc_epilogue_done();
+}
+
+__global__ void __launch_bounds__(kTT, 1)
+fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
+  extern __shared__ uint8_t tc_raw[];
+  __shared__ TcJobDev J;
+  __shared__ __align__(8) uint64_t bars[kTMaxStages + 1];
+  __shared__ float bias_s[kTMaxN];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[kTT / 32];
+  __shared__ float lvred[kTT / 32][64];
+  __shared__ uint32_t keys[8];
+  __shared__ float sl_s[64], scal_s[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + blockIdx.x);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = tid; i < (int)(sizeof(TcJobDev) / 4); i += kTT) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i <= kTMaxStages; ++i) t_mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(t_smem(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  t_fence_before();
+  __syncthreads();
+  t_fence_after();
+  TcRing R;
+  R.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+  R.empty = &bars[0]; R.accfull = &bars[kTMaxStages]; R.bias_s = bias_s;
+  R.par = 0; R.pend = 0; R.gemms = 0; R.tmem = tmem_base_s;
+
+  const int B = J.B, BP = J.BP, D = J.D, L = J.L, DR = J.DR, G = J.G, LD = J.LD, Lp = J.Lp;
+  float* __restrict__ ws = J.ws;
+  const int pm = J.pm_stride;
+  const int ne = J.n_enc, nd = J.n_dec;
+
+  // ---- flat (C ABI) parameter / moment vectors -> aligned copies W [K][Np], bias [Np] (+ m, v) and W^T [Np][Kp]
+  for (int net = 0; net < 2; ++net)
+    for (int i = 0; i < (net ? nd : ne); ++i) {
+      const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      for (int idx = tid; idx < Ly.K * Ly.N; idx += kTT) {
+        const int k = idx / Ly.N, n = idx - k * Ly.N;
+        const float p = J.params[Ly.flat_w + idx];
+        const size_t o = Ly.W + tc_w8(Ly, k, n);
+        ws[o] = p;
+        ws[o + pm] = J.adam_m[Ly.flat_w + idx];
+        ws[o + 2 * pm] = J.adam_v[Ly.flat_w + idx];
+        if (k < Ly.Kuse) ws[Ly.WT + (size_t)n * Ly.Kp + k] = p;
+      }
+      for (int n = tid; n < Ly.N; n += kTT) {
+        ws[Ly.Bv + n] = J.params[Ly.flat_b + n];
+        ws[Ly.Bv + pm + n] = J.adam_m[Ly.flat_b + n];
+        ws[Ly.Bv + 2 * pm + n] = J.adam_v[Ly.flat_b + n];
+      }
+      // the ones row of the layer input's feature-major copy: row Kuse (bias gradient = ones . dY)
+      for (int b = tid; b < BP; b += kTT) ws[Ly.in_T + (size_t)Ly.Kuse * BP + b] = b < B ? 1.0f : 0.0f;
+    }
+  // Encoder layer 0 rows d >= DR multiply exactly-zero padding columns (gradient exactly 0): untouched unless the
+  // caller supplied NON-zero Adam moments there, in which case they take the g = 0 Adam update every step.
+  const TcLayer& E0 = J.enc[0];
+  int nz = 0;
+  for (int idx = tid; idx < (E0.K - DR) * E0.N; idx += kTT) {
+    const int gi = E0.flat_w + DR * E0.N + idx;
+    nz |= (J.adam_m[gi] != 0.f || J.adam_v[gi] != 0.f) ? 1 : 0;
+  }
+  const bool decay_skipped = __syncthreads_or(nz) != 0;
+
+  uint32_t ck0 = 0, ck1 = 0;           // lanes 0,1 model-side chain, lanes 2,3 dataset-side chain
+  if (tid < 4) { const uint32_t* src = tid < 2 ? J.model_key : J.dataset_key; ck0 = src[0]; ck1 = src[1]; }
+  const int32_t step0 = J.step[0];
+  double b1t = pow((double)J.b1, (double)step0), b2t = pow((double)J.b2, (double)step0);
+  TcHyper hp; hp.lr = J.lr; hp.b1 = J.b1; hp.b2 = J.b2; hp.omb1 = J.omb1; hp.omb2 = J.omb2; hp.eps = J.adam_eps;
+  const float invB = 1.0f / (float)B, fB = (float)B;
+  const int row = q * 32 + lane;                 // accumulator row (TMEM lane) this thread drains
+  const uint32_t trow = R.tmem + ((uint32_t)(q * 32) << 16);
+  __syncthreads();
+
+  for (int64_t s = 0; s < n_steps; ++s) {
+#ifdef VAE_TC_PROFILE
+    const long long _ts = clock64();
+#endif
+    // ---- keys of this step (vae.py:125, datasets.py:51)
+    if (tid < 4) {
+      uint32_t x0 = (uint32_t)(tid & 1), x1 = (uint32_t)(tid & 1) + 2u;
+      threefry2x32(ck0, ck1, x0, x1);
+      const uint32_t used = tid < 2 ? x0 : x1, carry = tid < 2 ? x1 : x0;
+      const uint32_t other = __shfl_xor_sync(0xFu, carry, 1);
+      ck0 = (tid & 1) ? other : carry; ck1 = (tid & 1) ? carry : other;
+      keys[tid] = used;                            // [lat0 lat1 bat0 bat1]
+    }
+    b1t *= (double)J.b1; b2t *= (double)J.b2;
+    hp.ibc1 = 1.0f / (1.0f - (float)b1t); hp.ibc2 = 1.0f / (1.0f - (float)b2t);
+    if (tid < L) sl_s[tid] = expf(0.5f * J.params[J.off_lv + tid]);
+    if (tid == 0) {
+      const float e = J.tunable ? J.params[J.off_eps] * J.eps0 : J.eps0;
+      scal_s[0] = e; scal_s[1] = expf(0.5f * e); scal_s[2] = expf(-e);
+    }
+    __syncthreads();
+    // ================= random draws: eps (B, L + D) row-major (model.py:227) and the generator normals (B, G)
+    {
+      const uint32_t lk0 = keys[0], lk1 = keys[1], bk0 = keys[2], bk1 = keys[3];
+      const int n_e = B * LD, half_e = (n_e + 1) >> 1, n_d = B * G, half_d = (n_d + 1) >> 1;
+      float* z = ws + J.ws_z; float* gn = ws + J.ws_gn;
+      for (int w = tid; w < half_e + half_d; w += kTT) {
+        if (w < half_e) {
+          const int j = w, j2 = w + half_e;
+          uint32_t x0 = (uint32_t)j, x1 = j2 < n_e ? (uint32_t)j2 : 0u;
+          threefry2x32(lk0, lk1, x0, x1);
+          z[j] = normal_from_bits(x0);
+          if (j2 < n_e) z[j2] = normal_from_bits(x1);
+        } else {
+          const int j = w - half_e, j2 = j + half_d;
+          uint32_t x0 = (uint32_t)j, x1 = j2 < n_d ? (uint32_t)j2 : 0u;
+          threefry2x32(bk0, bk1, x0, x1);
+          gn[j] = normal_from_bits(x0);
+          if (j2 < n_d) gn[j2] = normal_from_bits(x1);
+        }
+      }
+    }
+    __syncthreads();
+    // ================= generator transform (bit-exact op order, oracle/datasets.py): x -> batch-major + feature-major
+    for (int b = tid; b < B; b += kTT) {
+      const float* gr = ws + J.ws_gn + (size_t)b * G;
+      auto xb = [&](int j) -> float& { return ws[E0.in_bm + ((size_t)(j >> 3) * BP + b) * 8 + (j & 7)]; };
+      float* xT = ws + E0.in_T + b;
+      if (J.kind == VAE_DATA_SPHERE) {
+        float acc = 0.f;
+        for (int j = 0; j < J.dd; ++j) { const float v = gr[j]; const float sq = __fmul_rn(v, v); acc = j == 0 ? sq : __fadd_rn(acc, sq); }
+        const float rad = __fsqrt_rn(acc);
+        for (int j = 0; j < J.dd; ++j) { const float v = __fdiv_rn(gr[j], rad); xb(j) = v; xT[(size_t)j * BP] = v; }
+      } else if (J.kind == VAE_DATA_LINEAR_GAUSSIAN) {
+        for (int i = 0; i < J.dd; ++i) {
+          float acc = __fmul_rn(J.A[i * G], gr[0]);
+          for (int k = 1; k < G; ++k) acc = __fadd_rn(acc, __fmul_rn(J.A[i * G + k], gr[k]));
+          xb(i) = acc; xT[(size_t)i * BP] = acc;
+        }
+      } else {
+        float acc = 0.f;
+        for (int j = 0; j < J.dd; ++j) {
+          const float v = gr[j]; xb(j) = v; xT[(size_t)j * BP] = v;
+          const float pr = __fmul_rn(v, J.A[j]); acc = j == 0 ? pr : __fadd_rn(acc, pr);
+        }
+        const float sg = det_sigmoid(acc);
+        xb(J.dd) = sg; xT[(size_t)J.dd * BP] = sg;
+      }
+    }
+    __syncthreads();
+#ifdef VAE_TC_PROFILE
+    if (tid == 0 && blockIdx.x == 0) g_tc_prof[6] += clock64() - _ts;
+#endif
+
+    // ================= forward: encoder then decoder
+    float kl_part = 0.f, r2 = 0.f, rz = 0.f;
+    for (int net = 0; net < 2; ++net) {
+      const int nl = net ? nd : ne;
+      for (int i = 0; i < nl; ++i) {
+        const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+        const int kpad = i == 0 ? t_up8(Ly.Kuse) : Ly.Kp;
+        tc_gemm(R, TcOperand{ws + Ly.in_bm, BP, 1}, BP, 1, TcOperand{ws + Ly.WT, Ly.Kp, 0}, Ly.N, Ly.Np, kpad, ws + Ly.Bv, Ly.N);
+        TC_T0();
+        const float* bias = R.bias_s;
+        const bool last = i == nl - 1;
+        uint64_t mlo = 0, mhi = 0;                       // relu'(output) bytes of this thread's column groups (hidden layers)
+        for (int g = half; g < (Ly.Np >> 3); g += 2) {
+          float acc[8];
+          t_ld8_sum(trow + (uint32_t)(g * 8), acc);
+          if (row >= BP) continue;
+          const int n0 = g * 8;
+          const bool vrow = row < B;
+          const size_t gofs = ((size_t)g * BP + row) * 8;           // group-major batch-major element (row, 8 g)
+          if (!last) {                                   // hidden layer: relu(x W + b) (networks.py:33-39)
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (vrow && n0 + j < Ly.N) ? fmaxf(acc[j] + bias[n0 + j], 0.f) : 0.f;
+            t_stg8(ws + Ly.out_bm + gofs, y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n0 + j < Ly.N) ws[Ly.out_T + (size_t)(n0 + j) * BP + row] = y[j];
+            uint64_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bits |= (uint64_t)(y[j] > 0.f ? 1u : 0u) << j;
+            const int idx = g >> 1;
+            if (idx < 8) mlo |= bits << (idx * 8); else mhi |= bits << ((idx - 8) * 8);
+          } else if (net == 0) {                         // mu; zs = mu + exp(lv/2) z1 (networks.py:67-74)
+            const TcLayer& D0 = J.dec[0];
+            float mu[8], zs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool ok = vrow && n0 + j < L;
+              mu[j] = ok ? acc[j] + bias[n0 + j] : 0.f;
+              kl_part = fmaf(mu[j], mu[j], kl_part);
+              zs[j] = ok ? fmaf(sl_s[n0 + j], ws[J.ws_z + (size_t)row * LD + n0 + j], mu[j]) : 0.f;
+            }
+            t_stg8(ws + J.ws_mu + gofs, mu);
+            t_stg8(ws + D0.in_bm + gofs, zs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n0 + j < L) ws[D0.in_T + (size_t)(n0 + j) * BP + row] = zs[j];
+          } else {                                       // x_hat, residual, d x_hat (networks.py:81-83, 95-98)
+            const float sd = scal_s[1], gscale = scal_s[2] * invB;
+            float gq[8], xv[8];
+            t_ldg8(ws + E0.in_bm + gofs, xv);            // x has the same group-major layout (columns >= DR are zero)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int d = n0 + j;
+              float gv = 0.f;
+              if (vrow && d < D) {
+                const float z2 = ws[J.ws_z + (size_t)row * LD + L + d];
+                const float xh = fmaf(z2, sd, acc[j] + bias[d]);
+                const float r = xh - (d < DR ? xv[j] : 0.f);
+                r2 = fmaf(r, r, r2); rz = fmaf(r, z2, rz);
+                gv = r * gscale;
+              }
+              gq[j] = gv;
+            }
+            t_stg8(ws + J.ws_gbm[0] + gofs, gq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n0 + j < D) ws[J.ws_gT[0] + (size_t)(n0 + j) * BP + row] = gq[j];
+          }
+        }
+        if (!last && row < BP)                           // [BP][2 halves][16 bytes]: read back by the same (row, half) thread
+          reinterpret_cast<uint4*>(ws + Ly.out_mask)[row * 2 + half] =
+              make_uint4((uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32));
+        tc_epilogue_done();
+        TC_ACC(4);
+      }
+    }
+    // ================= loss (networks.py:94-98) and the decoder log-variance parameter
+    {
+      const float s_r2 = tc_block_sum(r2, red), s_rz = tc_block_sum(rz, red), s_mu2 = tc_block_sum(kl_part, red);
+      if (tid == 0) {
+        const float e = scal_s[0], sd = scal_s[1], inv_var = scal_s[2];
+        float klc = 0.f;
+        for (int l = 0; l < L; ++l) { const float lv = J.params[J.off_lv + l]; klc += 1.f + lv - expf(lv); }
+        const float dkl = (-0.5f * klc * fB + 0.5f * s_mu2) * invB;
+        const float mse = (0.5f * inv_var * s_r2 + 0.5f * (1.8378770664093453f + e) * fB * (float)D) * invB;
+        J.loss_out[s] = dkl + mse;
+        if (J.tunable) {
+          const float g = J.eps0 * invB * (-0.5f * inv_var * s_r2 + 0.5f * fB * (float)D + 0.5f * sd * inv_var * s_rz);
+          float m = J.adam_m[J.off_eps], v = J.adam_v[J.off_eps];
+          J.params[J.off_eps] = t_adam(J.params[J.off_eps], m, v, g, hp);
+          J.adam_m[J.off_eps] = m; J.adam_v[J.off_eps] = v;
+        }
+      }
+    }
+    // ================= backward: decoder (dY of layer i in gbm[cur] / gT[cur]), latent, encoder
+    int cur = 0;
+    for (int net = 1; net >= 0; --net) {
+      const int nl = net ? nd : ne;
+      for (int i = nl - 1; i >= 0; --i) {
+        const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+        const float* gbm = ws + J.ws_gbm[cur];
+        const float* gT = ws + J.ws_gT[cur];
+        const bool need_dx = !(net == 0 && i == 0);
+        if (need_dx) {
+          // dX[b][k] = sum_n dY[b][n] W[k][n] with the OLD weights (Adam of this layer runs after)
+          const bool latent = net == 1 && i == 0;       // dzs: -> d lv partials, dmu = dzs + mu / B
+          uint64_t mlo = 0, mhi = 0;                     // relu'(layer input) bytes of this thread's (row, half) column groups
+          if (!latent && row < BP) {
+            const uint4 mk = reinterpret_cast<const uint4*>(ws + Ly.in_mask)[row * 2 + half];
+            mlo = (uint64_t)mk.x | ((uint64_t)mk.y << 32); mhi = (uint64_t)mk.z | ((uint64_t)mk.w << 32);
+          }
+          tc_gemm(R, TcOperand{gbm, BP, 1}, BP, 1, TcOperand{ws + Ly.W, Ly.K, 1}, Ly.K, Ly.Kp, Ly.Np);
+          TC_T0();
+          float* obm = ws + J.ws_gbm[cur ^ 1];
+          float* oT = ws + J.ws_gT[cur ^ 1];
+          for (int g = half; g < (Ly.Kp >> 3); g += 2) {
+            float acc[8];
+            t_ld8_sum(trow + (uint32_t)(g * 8), acc);
+            const int k0 = g * 8;
+            const bool vrow = row < B;
+            const size_t gofs = ((size_t)g * BP + (row < BP ? row : 0)) * 8;
+            float o[8];
+            if (!latent) {
+              const int idx = g >> 1;
+              const uint32_t bits = (uint32_t)((idx < 8 ? mlo >> (idx * 8) : mhi >> ((idx - 8) * 8)) & 0xFFu);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = (vrow && ((bits >> j) & 1u)) ? acc[j] : 0.f;
+            } else {
+              float pr[8], muv[8];
+              t_ldg8(ws + J.ws_mu + gofs, muv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool ok = vrow && k0 + j < L;
+                const float dz = ok ? acc[j] : 0.f;
+                pr[j] = ok ? dz * ws[J.ws_z + (size_t)row * LD + k0 + j] : 0.f;
+                o[j] = ok ? fmaf(muv[j], invB, dz) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float sum = warp_sum(pr[j]);
+                if (lane == 0) lvred[warp][k0 + j] = sum;
+              }
+            }
+            if (row < BP) {
+              t_stg8(obm + gofs, o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (k0 + j < Ly.K) oT[(size_t)(k0 + j) * BP + row] = o[j];
+            }
+          }
+          tc_epilogue_done();
+          TC_ACC(5);
+          if (latent && tid < L) {          // g_lv[l] = sum_b dzs z1 * 0.5 s_l - 0.5 (1 - e^lv_l)
+            const int gsel = (tid >> 3) & 1;  // column group g was drained by the warps with half == g & 1
+            float a = 0.f;
+            for (int w = 0; w < 4; ++w) a += lvred[4 * gsel + w][tid];
+            const float lv = J.params[J.off_lv + tid];
+            float m = J.adam_m[J.off_lv + tid], v = J.adam_v[J.off_lv + tid];
+            J.params[J.off_lv + tid] = t_adam(lv, m, v, a * 0.5f * sl_s[tid] - 0.5f * (1.f - expf(lv)), hp);
+            J.adam_m[J.off_lv + tid] = m; J.adam_v[J.off_lv + tid] = v;
+          }
+        }
+        tc_dw(R, ws, Ly, gT, BP, pm, hp);
+        cur ^= need_dx ? 1 : 0;
+      }
+    }
+    if (decay_skipped) {
+      for (int idx = tid; idx < (E0.K - DR) * E0.N; idx += kTT) {
+        float* P = ws + E0.W + tc_w8(E0, DR + idx / E0.N, idx % E0.N);
+        float m = P[pm], v = P[2 * pm];
+        P[0] = t_adam(P[0], m, v, 0.f, hp); P[pm] = m; P[2 * pm] = v;
+      }
+    }
+    __syncthreads();
+#ifdef VAE_TC_PROFILE
+    if (tid == 0 && blockIdx.x == 0) g_tc_prof[7] += clock64() - _ts;
+#endif
+  }
+
+  // ---- aligned copies -> flat (C ABI) vectors
+  for (int net = 0; net < 2; ++net)
+    for (int i = 0; i < (net ? nd : ne); ++i) {
+      const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      for (int idx = tid; idx < Ly.K * Ly.N; idx += kTT) {
+        const int k = idx / Ly.N, n = idx - k * Ly.N;
+        const size_t o = Ly.W + tc_w8(Ly, k, n);
+        J.params[Ly.flat_w + idx] = ws[o];
+        J.adam_m[Ly.flat_w + idx] = ws[o + pm];
+        J.adam_v[Ly.flat_w + idx] = ws[o + 2 * pm];
+      }
+      for (int n = tid; n < Ly.N; n += kTT) {
+        J.params[Ly.flat_b + n] = ws[Ly.Bv + n];
+        J.adam_m[Ly.flat_b + n] = ws[Ly.Bv + pm + n];
+        J.adam_v[Ly.flat_b + n] = ws[Ly.Bv + 2 * pm + n];
+      }
+    }
+  if (tid == 0) J.step[0] = step0 + (int32_t)n_steps;
+  if (tid < 4 && (tid & 1) == 0) { uint32_t* dst = tid < 2 ? J.model_key : J.dataset_key; dst[0] = ck0; dst[1] = ck1; }
+  t_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(R.tmem));
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Workspace layout (floats).  Every offset is a multiple of 4 floats (16-byte cp.async); every row stride a
+// multiple of 8.  The caller zero-fills the workspace once (padding rows / columns are never written).
+static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
+  Layout Lo;
+  if (make_layout(&j.desc, &Lo)) return 0;
+  const VaeDesc& d = j.desc;
+  const VaeDataDesc& g = j.data;
+  const int B = d.batch, BP = t_up8(B), L = d.latent_dim, D = d.data_dim;
+  const int DR = g.dim + (g.kind == VAE_DATA_SIGMOID ? 1 : 0);
+  const int G = g.kind == VAE_DATA_LINEAR_GAUSSIAN ? g.intrinsic_dim : g.dim;
+  TcJobDev J;
+  memset(&J, 0, sizeof(J));
+  size_t off = 0;
+  auto take = [&](size_t n) { const size_t r = off; off += (n + 7) & ~(size_t)7; return (int32_t)r; };
+  J.B = B; J.BP = BP; J.D = D; J.L = L; J.DR = DR; J.kind = g.kind; J.G = G; J.dd = g.dim;
+  J.tunable = d.tunable_decoder_var; J.n_enc = Lo.n_enc; J.n_dec = Lo.n_dec;
+  J.Lp = t_up8(L); J.Dp = t_up8(D); J.LD = L + D;
+  J.off_lv = (int32_t)Lo.off_eps_p; J.off_eps = (int32_t)Lo.off_eps; J.n_flat = (int32_t)Lo.n_params;
+  int maxw = 8;
+  // aligned parameter region P; M and V repeat it pm_stride floats further
+  for (int net = 0; net < 2; ++net)
+    for (int i = 0; i < (net ? Lo.n_dec : Lo.n_enc); ++i) {
+      TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      const int* sz = net ? Lo.dec_sizes : Lo.enc_sizes;
+      Ly.K = sz[i]; Ly.N = sz[i + 1]; Ly.Kp = t_up8(Ly.K); Ly.Np = t_up8(Ly.N);
+      Ly.Kuse = (net == 0 && i == 0) ? DR : Ly.K;
+      Ly.flat_w = (int32_t)(net ? Lo.dec_w[i] : Lo.enc_w[i]); Ly.flat_b = (int32_t)(net ? Lo.dec_b[i] : Lo.enc_b[i]);
+      Ly.W = take((size_t)Ly.K * Ly.Np); Ly.Bv = take(Ly.Np);
+      if (Ly.Kp > maxw) maxw = Ly.Kp;
+      if (Ly.Np > maxw) maxw = Ly.Np;
+    }
+  J.pm_stride = (int32_t)off;
+  off *= 3;
+  for (int net = 0; net < 2; ++net)
+    for (int i = 0; i < (net ? Lo.n_dec : Lo.n_enc); ++i) {
+      TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      Ly.WT = take((size_t)Ly.Np * Ly.Kp);
+    }
+  // activations: layer i's input (batch-major [BP][Kp], feature-major [Kp + 8][BP]); outputs alias the next input
+  for (int net = 0; net < 2; ++net) {
+    const int nl = net ? Lo.n_dec : Lo.n_enc;
+    for (int i = 0; i < nl; ++i) {
+      TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      Ly.in_bm = take((size_t)BP * Ly.Kp); Ly.in_T = take((size_t)(Ly.Kp + 8) * BP);
+    }
+    for (int i = 0; i + 1 < nl; ++i) {
+      TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+      TcLayer& Nx = net ? J.dec[i + 1] : J.enc[i + 1];
+      Ly.out_bm = Nx.in_bm; Ly.out_T = Nx.in_T;
+      Ly.out_mask = take((size_t)BP * 8);               // [BP][32] bytes
+      Nx.in_mask = Ly.out_mask;
+    }
+  }
+  J.ws_z = take((size_t)BP * (L + D) + 8); J.ws_gn = take((size_t)BP * G + 8); J.ws_mu = take((size_t)BP * J.Lp);
+  for (int b = 0; b < 2; ++b) { J.ws_gbm[b] = take((size_t)BP * maxw); J.ws_gT[b] = take((size_t)(maxw + 8) * BP); }
+  if (o) {
+    *o = J;
+    o->params = j.params; o->adam_m = j.adam_m; o->adam_v = j.adam_v; o->step = j.step;
+    o->model_key = j.model_key; o->dataset_key = j.dataset_key; o->A = j.A; o->loss_out = j.loss_out;
+    o->ws = (float*)j.workspace;
+    const AdamHyper hp = make_adam_hyper(&j.desc);
+    o->eps0 = (float)j.desc.epsilon0; o->lr = hp.lr; o->b1 = hp.b1; o->b2 = hp.b2; o->omb1 = hp.omb1; o->omb2 = hp.omb2;
+    o->adam_eps = hp.eps;
+  }
+  return off;
+}
+
+// 1 if the tensor-core kernel can run the job (then *ws_bytes = its workspace need)
+int mlp_tc_supported(const VaeTrainJob* j, size_t* ws_bytes) {
+  const VaeDesc& d = j->desc;
+  const VaeDataDesc& g = j->data;
+  if (d.n_enc_hidden + d.n_dec_hidden == 0 || d.sig_decoder || g.kind == VAE_DATA_SIGMOID) return 0;
+  Layout Lo;
+  if (make_layout(&d, &Lo)) return 0;
+  const int width = g.dim + g.padding_dim;
+  if (width != d.data_dim || d.latent_dim > 63 || d.batch > 128 || d.batch < 1) return 0;
+  if (Lo.max_width > kTMaxN - 8 || Lo.n_params >= (1ll << 30)) return 0;      // N <= 208 incl. the bias column / row
+  if (ws_bytes) *ws_bytes = tc_fill(*j, nullptr) * sizeof(float);
+  return 1;
+}
+
+size_t mlp_tc_job_bytes() { return sizeof(TcJobDev); }
+
+int mlp_tc_fill_job(const VaeTrainJob& j, void* out) {
+  return tc_fill(j, (TcJobDev*)out) ? 0 : VAE_ERR_INVALID;
+}
+
+int mlp_tc_prepare() {
+  cudaFuncAttributes fa;
+  VAE_CUDA_OK(cudaFuncGetAttributes(&fa, fused_mlp_tc_kernel));
+  VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024 - (int)fa.sharedSizeBytes));
+  if ((size_t)kTSmemBytes + fa.sharedSizeBytes > (size_t)227 * 1024) {
+    set_error("fused_mlp_tc_kernel needs %zu bytes of shared memory", (size_t)kTSmemBytes + fa.sharedSizeBytes);
+    return VAE_ERR_INVALID;
+  }
+  return 0;
+}
+
+int mlp_tc_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s) {
+  fused_mlp_tc_kernel<<<plan->n_jobs, kTT, kTSmemBytes, s>>>((const TcJobDev*)plan->d_jobs, n_steps);
+  VAE_LAUNCH_OK("fused_mlp_tc_kernel");
+  return 0;
+}
+
+#ifdef VAE_TC_PROFILE
+extern "C" int vae_tc_profile(long long* out16, int reset) {
+  long long z[16] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(z));
+  if (reset) cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  return 0;
+}
+#endif
+
+}  // namespace vae
