@@ -366,9 +366,19 @@ def tf32_peak(ctx):
     return 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
-def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key):
+def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key, tensor_peak=None):
     flop_step = spec.flops_per_step()
     achieved = flop_step * n_models * K / (ms_launch * 1e-3) / 1e12            # per GPU, algorithmic flops only
+    if tensor_peak is not None:       # the tcgen05 3xTF32 kernel (fused_mlp_tc.cu)
+        return {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": traffic_of(traffic_key),
+                "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                                f"'{traffic_key}' in profiles/traffic.json (null = not captured for this exact command)",
+                "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one GPU over the median "
+                        f"launch; peak = cuBLAS TF32 GEMM measured in this run ({tensor_peak:.0f} TFLOP/s; MEASURED_PEAKS.json "
+                        "holds only bf16).  FP32-level accuracy costs three TF32 MMAs per product (frac <= 1/3 by construction) "
+                        "and the step is a serial chain of 23 small GEMMs per model on ONE SM each (M = 128 batch tile, N <= 208, "
+                        "K <= 200): the kernel is shared-memory-bandwidth / store-bandwidth bound, see DESIGN.md 4.2b"}
     return {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic_of(traffic_key),
@@ -378,6 +388,9 @@ def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key):
                     f"median launch; peak = FFMA probe measured in this run ({peak:.1f} TFLOP/s); RNG work "
                     f"({spec.normals_per_step()} threefry normals/model-step) is not counted as flops",
             "normals_per_sec_per_gpu": spec.normals_per_step() * n_models * K / (ms_launch * 1e-3)}
+
+
+_TF32_PEAK = {}
 
 
 def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states=False):
@@ -397,12 +410,19 @@ def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states
     if not bool(torch.isfinite(loss_dev).all()):
         raise SystemExit(f"bench.py: non-finite loss in the timed region ({workload})")
     total = n_models * ctx.world
+    tensor_peak = None
+    if runs.plan.cls == 2 and runs.plan.cluster == 0:          # hidden-layer pack on the tensor-core kernel
+        if "v" not in _TF32_PEAK:
+            _TF32_PEAK["v"] = tf32_peak(ctx)
+        tensor_peak = _TF32_PEAK["v"]
     out = {"value": total * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
            "models_per_gpu": n_models, "samples_per_sec": total * K / (ms * 1e-3) * specs[0].batch_size,
            "timing": {"repeats": R, "window_ms": window, "launch_ms_median": ms},
            "launch_plan": {"class": runs.plan.cls, "models_per_cta": runs.plan.gm, "cluster": runs.plan.cluster},
            "gpu_launches": int(launches),
-           "roofline": pack_roofline(specs[0], n_models, K, ms, peak, f"{workload}_m{n_models}_k{K}")}
+           "kernel": ("fused_mlp_tc_kernel (tcgen05 3xTF32, one CTA per model)" if tensor_peak is not None else
+                      "fused_mlp_kernel (FP32 FFMA, one cluster per model)" if runs.plan.cls == 2 else "fused_small_kernel"),
+           "roofline": pack_roofline(specs[0], n_models, K, ms, peak, f"{workload}_m{n_models}_k{K}", tensor_peak)}
     if want_states:
         return out, runs, specs, states
     del runs

@@ -666,6 +666,90 @@ def test_fused_cluster_vs_oracle_loop(ops, lib, case):
     assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
 
 
+# ------------------------------------------------ tensor-core kernel for the same hidden-layer models (fused_mlp_tc.cu)
+
+@pytest.mark.parametrize("case", MLP_CASES, ids=lambda c: f"{c[0]}_dd{c[1]}_pd{c[2]}_L{c[3]}_h{len(c[4])}{len(c[5])}")
+def test_fused_tc_vs_oracle_loop(ops, lib, case, monkeypatch):
+    """The tcgen05 3xTF32 kernel's n steps == n iterations of model.py:221-222 in the float64 oracle: key chains
+    bit-exact, per-step loss rel 1e-5 (the TF32 hi/lo split with separate correction accumulators is as accurate as
+    the FP32 FFMA kernel: 3e-7 .. 2e-6 measured), parameters within 1e-3 lr per step."""
+    monkeypatch.setenv("VAE_MLP_TC", "1")
+    n = 12
+    d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
+    sc = ops.fused_scratch(1)
+    plan = ops.pack_prepare([job], sc)
+    assert plan.cls == 2 and plan.cluster == 0          # cluster 0 = the tensor-core kernel
+    ops.pack_train(plan, n)
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), tr.key)
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), ds.key)
+    assert int(st["step"]) == n
+    got = st["loss"].cpu().numpy().astype(np.float64)
+    ref = np.array(tr.train_losses, np.float64)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
+    assert_params_close(st["P"].cpu().numpy(), tr.params, n, d.lr, frac=0.95)
+    assert relerr(st["M"].cpu().numpy(), tr.m) <= 1e-4
+    assert relerr(st["V"].cpu().numpy(), tr.v) <= 1e-4
+
+
+def test_fused_tc_packed_chunked_and_deterministic(ops, lib, monkeypatch):
+    """Packing models into one launch (one CTA each) and splitting the steps over launches (the state travels through
+    the flat C-ABI vectors between launches) change nothing, bit for bit; and the FFMA cluster kernel agrees with the
+    tensor-core kernel to float32 round-off."""
+    monkeypatch.setenv("VAE_MLP_TC", "1")
+    n = 9
+    cases = (MLP_CASES[0], MLP_CASES[2], MLP_CASES[5], MLP_CASES[6])
+    singles, packed = [], []
+    for case in cases:
+        _, _, _, st, job = mlp_setup(ops, lib, case, n)
+        ops.train_fused([job], n, ops.fused_scratch(1))
+        singles.append(st)
+        packed.append(mlp_setup(ops, lib, case, n)[3:])
+    sc = ops.fused_scratch(len(cases))
+    for chunk in (2, 1, 6):
+        ops.train_fused([j for _, j in packed], chunk, sc)
+        torch.cuda.synchronize()
+    for a, (b, _) in zip(singles, packed):
+        for k in ("P", "M", "V", "mk", "dk", "step"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a["loss"][3:9], b["loss"][:6])
+    monkeypatch.setenv("VAE_MLP_TC", "0")
+    for case, a in zip(cases, singles):
+        _, _, _, st, job = mlp_setup(ops, lib, case, n)
+        ops.train_fused([job], n, ops.fused_scratch(1))
+        torch.cuda.synchronize()
+        la, lb = a["loss"].cpu().numpy().astype(np.float64), st["loss"].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(la - lb) / np.abs(lb)) <= REL_STEP
+
+
+def test_fused_tc_nonzero_moments_on_padding_rows(ops, lib, monkeypatch):
+    monkeypatch.setenv("VAE_MLP_TC", "1")
+    n = 8
+    case = MLP_CASES[1]
+    d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
+    rng = np.random.default_rng(9)
+    m0 = (rng.standard_normal(d.n_params) * 1e-2).astype(np.float32)
+    v0 = (rng.random(d.n_params) * 1e-4).astype(np.float32)
+    tr.m[:] = m0
+    tr.v[:] = v0
+    st["M"].copy_(dev(m0))
+    st["V"].copy_(dev(v0))
+    pad_rows = slice(case[1] * 200, d.data_dim * 200)
+    p_before = st["P"].cpu().numpy().copy()
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    torch.cuda.synchronize()
+    tr.train(10 ** 9, start=0, stop=n, events=False)
+    got = st["P"].cpu().numpy()
+    assert np.abs(got[pad_rows] - p_before[pad_rows]).max() > 1e-5
+    np.testing.assert_allclose(got[pad_rows], tr.params[pad_rows], rtol=0, atol=n * 1e-3 * d.lr)
+    assert relerr(st["M"].cpu().numpy()[pad_rows], tr.m[pad_rows]) <= 1e-5
+    assert relerr(st["V"].cpu().numpy()[pad_rows], tr.v[pad_rows]) <= 1e-5
+    got_l = st["loss"].cpu().numpy().astype(np.float64)
+    ref_l = np.array(tr.train_losses, np.float64)
+    assert np.max(np.abs(got_l - ref_l) / np.abs(ref_l)) <= REL_STEP
+
+
 def test_fused_cluster_nonzero_moments_on_padding_rows(ops, lib):
     """As test_fused_small_nonzero_moments_on_padding_rows, for the cluster kernel: encoder layer-0 rows that
     multiply the zero padding columns keep decaying under flax Adam when their moments are non-zero."""
@@ -692,11 +776,12 @@ def test_fused_cluster_nonzero_moments_on_padding_rows(ops, lib):
 
 
 def test_fused_cluster_size_16_equals_8(ops, lib, monkeypatch):
-    """Small packs run each model on a 16-CTA (non-portable) cluster, larger packs on 8 or 4 CTAs
+    """(FFMA cluster kernel, VAE_MLP_TC=0.)  Small packs run each model on a 16-CTA (non-portable) cluster, larger packs on 8 or 4 CTAs
     (fused_mlp.cu:mlp_pick_cluster).  Column slices change, the arithmetic per output element
     does not: both cluster sizes must agree bit for bit (results never depend on the pack size)."""
     n = 10
     out = {}
+    monkeypatch.setenv("VAE_MLP_TC", "0")
     for cs in ("1", "2", "4", "8", "16"):
         monkeypatch.setenv("VAE_MLP_CLUSTER", cs)
         res = []

@@ -79,25 +79,67 @@ def test_kmajor_operands_and_raw_fp32_truncation(lib):
     assert er > 20 * et
 
 
-def test_mn_major_a_and_b(lib):
-    """The dW form: A = X^T and B = dY^T, both read MN-major from batch-major images (rows = batch = K)."""
-    rng = np.random.default_rng(1)
-    kb, n = 24, 104                                                     # 3 k-steps of 8 batch rows
-    X = trunc_tf32(rng.standard_normal((kb, 128)).astype(np.float32))   # [b][k_feature] : M = 128 features
-    dY = trunc_tf32(rng.standard_normal((kb, 128)).astype(np.float32))  # [b][n_feature] : N = 104 of 128 stored
-    got = run(lib, sw128_image(X), sw128_image(dY), desc_hi(kb * 128, 1024), desc_hi(kb * 128, 1024),
-              idesc(n, a_mn=True, b_mn=True), kb // 8, 1024, 1024, n)
-    ref = X.astype(np.float64).T @ dY.astype(np.float64)[:, :n]
-    assert relerr(got, ref) <= 2e-6
+def image_rows(mat, row_bytes, swz_shift, swz_mask):
+    """K-major image with rows of `row_bytes` (16-byte chunk index XOR ((row >> swz_shift) & swz_mask)); matrices wider
+    than one row are stored as consecutive [K block][row][row_bytes] blocks."""
+    rows, cols = mat.shape
+    per = row_bytes // 4
+    img = np.zeros((cols // per, rows, per // 4, 4), np.float32)
+    for a in range(cols // per):
+        blk = mat[:, per * a:per * a + per].reshape(rows, per // 4, 4)
+        for r in range(rows):
+            perm = np.arange(per // 4) ^ ((r >> swz_shift) & swz_mask)
+            img[a, r][perm] = blk[r]
+    return img.reshape(-1)
 
 
-def test_kmajor_a_mn_major_b(lib):
-    """The forward form with W stored (in, out): A = activations K-major, B = W read MN-major (rows = k)."""
+def desc_k(sbo, layout):
+    return (1 << 16) | ((sbo >> 4) << 32) | (1 << 46) | (layout << 61)
+
+
+@pytest.mark.parametrize("n", [104, 208])
+def test_kmajor_swizzle_64b_rows(lib, n):
+    """How fused_mlp_tc.cu stages ROW-MAJOR operands: TMA box {16 floats, rows} with SWIZZLE_64B -> 64-byte rows,
+    descriptor layout 4, SBO 512; the second K = 8 step starts 32 bytes further."""
+    rng = np.random.default_rng(5)
+    A = trunc_tf32(rng.standard_normal((128, 16)).astype(np.float32))
+    B = trunc_tf32(rng.standard_normal((n, 16)).astype(np.float32))
+    got = run(lib, image_rows(A, 64, 1, 3), image_rows(B, 64, 1, 3), desc_k(512, 4), desc_k(512, 4), idesc(n), 2, 32, 32, n)
+    assert relerr(got, A.astype(np.float64) @ B.astype(np.float64).T) <= 2e-6
+
+
+@pytest.mark.parametrize("n", [104, 208])
+def test_kmajor_swizzle_32b_groups(lib, n):
+    """How it stages GROUP-MAJOR operands ([k / 8][row][8]): TMA box {8 floats, rows, 2 groups} with SWIZZLE_32B ->
+    two [row][32-byte] blocks, descriptor layout 6, SBO 256; the second K = 8 step is the next block (32 x rows bytes)."""
+    rng = np.random.default_rng(6)
+    A = trunc_tf32(rng.standard_normal((128, 16)).astype(np.float32))
+    B = trunc_tf32(rng.standard_normal((n, 16)).astype(np.float32))
+    got = run(lib, image_rows(A, 32, 2, 1), image_rows(B, 32, 2, 1), desc_k(256, 6), desc_k(256, 6), idesc(n), 2, 128 * 32, n * 32, n)
+    assert relerr(got, A.astype(np.float64) @ B.astype(np.float64).T) <= 2e-6
+
+
+def test_mn_major_tf32_needs_the_32b_base_swizzle(lib):
+    """Why the kernel keeps feature-major copies instead of reading X^T / dY^T MN-major from the batch-major arrays:
+    for kind::tf32 an MN-major operand is only read correctly from the SWIZZLE_128B_BASE32B layout (layout 1: 4-row
+    atoms, 32-byte chunk index XOR (row % 4), SBO 512); with the plain SWIZZLE_128B image the MMA returns zeros."""
     rng = np.random.default_rng(2)
     k, n = 32, 104
     A = trunc_tf32(rng.standard_normal((128, k)).astype(np.float32))
-    W = trunc_tf32(rng.standard_normal((k, 128)).astype(np.float32))    # [k][n], 104 of 128 columns used
-    got = run(lib, sw128_image(A), sw128_image(W), desc_hi(16, 1024), desc_hi(k * 128, 1024), idesc(n, b_mn=True),
-              4, 32, 1024, n)
+    W = trunc_tf32(rng.standard_normal((k, 128)).astype(np.float32))    # [k][n]: B read MN-major (rows = K)
     ref = A.astype(np.float64) @ W.astype(np.float64)[:, :n]
-    assert relerr(got, ref) <= 2e-6
+    ka = desc_hi(16, 1024)
+
+    def base32_image(mat):
+        rows, cols = mat.shape
+        img = np.zeros((cols // 32, rows, 4, 8), np.float32)
+        for a in range(cols // 32):
+            blk = mat[:, 32 * a:32 * a + 32].reshape(rows, 4, 8)
+            for r in range(rows):
+                img[a, r][np.arange(4) ^ (r % 4)] = blk[r]
+        return img.reshape(-1)
+    mn = lambda lbo, sbo, layout: ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1 << 46) | (layout << 61)
+    good = run(lib, sw128_image(A), base32_image(W), ka, mn(k * 128, 512, 1), idesc(n, b_mn=True), 4, 32, 1024, n)
+    assert relerr(good, ref) <= 2e-6
+    bad = run(lib, sw128_image(A), sw128_image(W), ka, mn(k * 128, 1024, 2), idesc(n, b_mn=True), 4, 32, 1024, n)
+    assert np.count_nonzero(bad) == 0

@@ -27,10 +27,15 @@ int mlp_tc_fill_job(const VaeTrainJob& j, void* out);
 int mlp_tc_prepare();
 int mlp_tc_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
 
-// VAE_MLP_TC=0 keeps hidden-layer models on the FP32 FFMA cluster kernel (A/B runs, bit-identity tests)
-static bool use_mlp_tc(const VaeTrainJob* j, size_t* ws) {
+// Which kernel runs a class-2 pack.  The tensor-core kernel (one CTA per model, ~430 us per step however many models
+// are resident) wins on THROUGHPUT once a pack is large enough to fill the GPU with single-CTA models -- measured on
+// B200: 148 models 282 k steps/s vs 155 k for the FFMA kernel, break-even near 64 models -- while the FFMA cluster
+// kernel (8 - 16 CTAs per model, 147 - 169 us per step) wins on LATENCY for small packs.  VAE_MLP_TC=1 / 0 forces.
+constexpr int kMlpTcMinJobs = 64;
+static bool use_mlp_tc(const VaeTrainJob* j, size_t* ws, int n_jobs) {
   const char* e = getenv("VAE_MLP_TC");
-  if (!e || e[0] != '1') return false;          // opt-in while the tensor-core kernel is being brought up
+  if (e && e[0] == '0') return false;
+  if (!(e && e[0] == '1') && n_jobs < kMlpTcMinJobs) return false;
   return mlp_tc_supported(j, ws) != 0;
 }
 }  // namespace vae
@@ -70,7 +75,7 @@ int vae_train_fused_resident_jobs(const VaeTrainJob* job) {
   }
   size_t smem = 0, smem4 = 0;
   if (!vae::mlp_supported(job, &smem, nullptr, &smem4)) return 0;
-  if (vae::use_mlp_tc(job, nullptr)) {                              // tensor-core kernel: one CTA (= model) per SM
+  if (vae::use_mlp_tc(job, nullptr, 1 << 20)) {                     // a GPU-filling pack runs on the tensor-core kernel: one CTA (= model) per SM
     int dev = 0, sms = 0;
     VAE_CUDA_OK(cudaGetDevice(&dev));
     VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -112,7 +117,7 @@ int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, s
   } else {
     // class 2 on the tensor cores: one CTA per model (every job must qualify, else the FFMA cluster kernel runs the pack)
     bool tc = true;
-    for (int i = 0; i < n_jobs && tc; ++i) tc = vae::use_mlp_tc(&jobs[i], nullptr);
+    for (int i = 0; i < n_jobs && tc; ++i) tc = vae::use_mlp_tc(&jobs[i], nullptr, n_jobs);
     if (tc) {
       const size_t tjb = vae::mlp_tc_job_bytes();
       char* th = (char*)malloc((size_t)n_jobs * tjb);

@@ -29,14 +29,16 @@
 //                                          per element with either sign)
 // Only algorithmic flops (2MNK) are ever reported as useful work.
 //
-// Pipeline per GEMM: K is walked in chunks of 16 through a 3-stage shared-memory ring.  All 256 threads
-// stage a chunk: 16-byte cp.async copies from the row-major global operands into the canonical K-major
-// no-swizzle core-matrix layout (8 rows x 16 bytes, contiguous 128 bytes; LBO = 128 B between K chunks,
-// SBO = 512 B between 8-row groups) = the hi operand; each thread then derives the lo pieces of what it
-// copied; one thread issues the chunk's MMAs and a tcgen05.commit that frees the ring slot.  After the last
-// chunk the accumulator (128 lanes x N columns per M tile) is drained with tcgen05.ld by all 8 warps (lane
-// quarter = warp % 4, column groups split between the two warps of a quarter) into the fused epilogue:
-// bias + relu, relu mask, reparameterisation, loss partials, or Adam.
+// Pipeline per GEMM: K is walked in chunks of 16 through a shared-memory ring (3-4 stages, cut to the GEMM's
+// size).  One thread feeds the ring with TMA, ONE cp.async.bulk.tensor per operand and chunk: row-major operands
+// land as 64-byte rows (SWIZZLE_64B), group-major ones as two [row][32-byte] blocks (SWIZZLE_32B) -- the canonical
+// K-major layouts tcgen05 reads -- with rows / K beyond the matrix zero-filled.  All 512 threads turn the landed
+// chunk into hi = TF32(x) (in place) and lo = x - hi (position-preserving, so the swizzle does not matter); the
+// feeding thread then issues the chunk's MMAs and a tcgen05.commit that frees the ring slot.  After the last chunk
+// the accumulator (128 lanes x N columns per M tile) is drained with tcgen05.ld by all 16 warps (lane quarter =
+// warp % 4, column groups dealt round-robin to the four warps of a quarter) into the fused epilogue: bias + relu,
+// relu mask, reparameterisation, loss partials, or Adam.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -44,14 +46,19 @@
 
 namespace vae {
 
-constexpr int kTT = 256;                        // threads per CTA
+constexpr int kTT = 512;                        // threads per CTA
+constexpr int kTW = kTT / 32;                   // warps
+constexpr int kTCG = kTW / 4;                   // warps per TMEM lane quarter = column-group classes
 constexpr int kTKC = 16;                        // K elements per staged chunk (two K = 8 MMA steps)
 constexpr int kTMaxStages = 6;
 constexpr int kTMaxN = 208;                     // most B rows (accumulator columns) of one GEMM
-constexpr int kTATile = 128 * kTKC * 4;         // one M tile of A (hi or lo) per stage: 8 KB
 constexpr int kTRingBytes = 176 * 1024;         // the operand ring; a GEMM cuts it into stages of its own size
 constexpr int kTSmemBytes = kTRingBytes + 1024;
 constexpr int kTMaxL = VAE_MAX_HIDDEN + 1;
+// tensor maps of a model: per layer [W^T, W (group-major), input batch-major, input feature-major, dY feature-major],
+// then the two batch-major gradient buffers
+enum { TM_WT = 0, TM_W8 = 1, TM_INBM = 2, TM_INT = 3, TM_GT = 4, TM_PER_LAYER = 5 };
+constexpr int kTMaps = 2 * kTMaxL * TM_PER_LAYER + 2;
 
 __host__ __device__ constexpr int t_up8(int n) { return (n + 7) & ~7; }
 __host__ __device__ constexpr int t_up4(int n) { return (n + 3) & ~3; }
@@ -65,6 +72,7 @@ struct TcLayer {
   int32_t in_bm, in_T;             // layer input: batch-major [BP][Kp], feature-major [Kp + 8][BP] (row Kuse = ones)
   int32_t out_bm, out_T;           // layer output (hidden layers): batch-major [BP][Np], feature-major [Np + 8][BP]
   int32_t in_mask, out_mask;       // relu masks (output > 0) of the input / output activation: [BP][32] bytes, one per 8 columns
+  int32_t gcur;                    // which of the two gradient buffers holds this layer's dY in the backward pass
 };
 
 struct TcJobDev {
@@ -78,6 +86,7 @@ struct TcJobDev {
   int32_t n_flat;
   TcLayer enc[kTMaxL], dec[kTMaxL];
   float eps0, lr, b1, b2, omb1, omb2, adam_eps;
+  alignas(64) CUtensorMap maps[kTMaps];   // read by TMA straight from the job table in global memory
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -106,20 +115,32 @@ __device__ __forceinline__ void t_mma(uint32_t tmem_d, uint64_t da, uint64_t db,
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major, no swizzle: LBO = 128 B (next 16-byte K chunk), SBO = 512 B (next 8-row group), version 1
-__device__ __forceinline__ uint64_t t_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+// K-major shared-memory operand descriptors for the two ways TMA lands a 16-float K chunk (version 1):
+//   row-major global operand  -> rows of 64 bytes, SWIZZLE_64B (layout 4): 8-row atoms 512 B apart (SBO); a K = 8
+//                                step is 32 bytes further inside the row
+//   group-major global operand -> two K groups of [row][32 bytes], SWIZZLE_32B (layout 6): 8-row atoms 256 B apart;
+//                                a K = 8 step is the next group block (32 x rows bytes further)
+__device__ __forceinline__ uint64_t t_desc(uint32_t smem_addr, int grouped) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((grouped ? 256 : 512) >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)(grouped ? 6 : 4) << 61);
 }
 // c = F32, a = b = TF32, both K-major, N >> 3 at [17,23), M = 128 (>> 4) at [24,29)
 __device__ __forceinline__ uint32_t t_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void t_cp16(uint32_t dst, const float* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void t_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void t_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void t_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// one chunk (16 K floats) of the operand's box rows: row-major operands are a 2-D map {K floats, rows} (box 16 x rows),
+// group-major ones a 3-D map {8 floats, rows, K groups} (box 8 x rows x 2)
+__device__ __forceinline__ void t_tma_chunk(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int chunk, int grouped) {
+  if (grouped)
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(0), "r"(2 * chunk) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(16 * chunk), "r"(0) : "memory");
+}
 // 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void t_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -177,129 +198,88 @@ __device__ __forceinline__ float t_adam(float p, float& m, float& v, float g, co
 
 #ifdef VAE_TC_PROFILE
 __device__ long long g_tc_prof[16];
+#define TC_LAPS() long long _tl = clock64()
+#define TC_LAP(i) do { if (blockIdx.x == 0) { const long long _n = clock64(); g_tc_prof[i] += _n - _tl; _tl = _n; } } while (0)
 #define TC_T0() const long long _t0 = clock64()
 #define TC_ACC(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_prof[i] += clock64() - _t0; } while (0)
 #else
 #define TC_T0() do {} while (0)
 #define TC_ACC(i) do {} while (0)
+#define TC_LAPS() do {} while (0)
+#define TC_LAP(i) do {} while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------ GEMM main loop
 struct TcRing {
   uint8_t* base;                  // kTRingBytes, 1024-byte aligned
+  uint64_t* full;                 // [kTMaxStages] TMA bytes of the slot have landed
+  uint64_t* ready;                // [kTMaxStages] the slot's hi / lo split is complete (one arrive per converter warp)
   uint64_t* empty;                // [kTMaxStages] ring slot free (tcgen05.commit of the MMAs that read it)
   uint64_t* accfull;              // accumulator complete
   float* bias_s;                  // [kTMaxN] bias of the running GEMM (forward epilogues)
-  uint32_t par;                   // bit s: parity of empty[s]'s next completion
+  uint32_t fpar;                  // bit s: parity of full[s]'s next completion      (converter threads)
+  uint32_t rpar;                  // bit s: parity of ready[s]'s next completion     (feeding thread)
+  uint32_t par;                   // bit s: parity of empty[s]'s next completion     (feeding thread)
   uint32_t pend;                  // bit s: a commit on empty[s] has not been waited for yet
   uint32_t gemms;                 // GEMMs finished so far
   uint32_t tmem;                  // tensor-memory base (M tile t accumulates at column 256 t)
 };
 
-template <int N>
-__device__ __forceinline__ void t_cp_wait_dyn(int n) {
-  if (n >= N) t_cp_wait<N>();
-  else if constexpr (N > 0) t_cp_wait_dyn<N - 1>(n);
-}
+// A GEMM operand: its tensor map (box = box_rows x 16 K floats), whether the global array is group-major, box rows.
+struct TcOperand { const CUtensorMap* tm; int grouped; int box_rows; };
 
-// A GEMM operand in global memory: rows x K floats.
-//   grouped = 0: row-major, element (r, k) at ptr[r * ld + k]                      (ld = row stride, a multiple of 4)
-//   grouped = 1: group-major [k / 8][r][8], element (r, k) at ptr[((k >> 3) * ld + r) * 8 + (k & 7)]   (ld = rows per group block)
-struct TcOperand { const float* ptr; int ld; int grouped; };
-__device__ __forceinline__ const float* tc_piece(const TcOperand& o, int r, int k) {      // k a multiple of 4
-  return o.grouped ? o.ptr + ((size_t)(k >> 3) * o.ld + r) * 8 + (k & 7) : o.ptr + (size_t)r * o.ld + k;
-}
-
-// D[m][n] = sum_k A[m][k] B[n][k]:  A rows [0, a_rows) (M tiles of 128), B rows [0, b_rows), k < kpad (multiple of 8).
-// n_mma (multiple of 8, >= b_rows): MMA N.  bias (may be null): n_bias floats copied to R.bias_s while the main loop runs.
-// The ring is cut into stages of this GEMM's own size, (128 m_tiles + up8(b_rows)) x 16 floats x {hi, lo}: 4 stages
-// for the single-tile GEMMs, 3 for the two-tile dW; chunk c + stages - 1 is in flight while chunk c is multiplied.
-// Thread -> piece mapping: consecutive lanes take the 8 rows of a core matrix (16 bytes apart in shared memory: a
-// quarter warp covers all 32 banks), then the next 16-byte K piece.
-// On return the accumulator is complete and visible to tcgen05.ld (all threads have waited).
-__device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int a_rows, int m_tiles,
-                                        const TcOperand Bm, int b_rows, int n_mma, int kpad,
+// D[m][n] = sum_k A[m][k] B[n][k], k < kpad (multiple of 8).  A: m_tiles M tiles of 128 rows out of A.box_rows; B:
+// B.box_rows rows, n_mma (multiple of 8) of them multiplied.  bias (may be null): n_bias floats copied to R.bias_s
+// while the main loop runs.  The ring is cut into stages of this GEMM's own size, (A.box_rows + B.box_rows) x 16
+// floats x {hi, lo}: [A hi][B hi][A lo][B lo]; up to stages - 1 chunks are in flight beyond the one being multiplied.
+// Roles: thread 0 feeds the ring (TMA) and issues the MMAs; warps 1..15 split the landed chunks into hi / lo and hand
+// them over through the `ready` barriers -- no block-wide barrier inside the loop, so the split of chunk c + 1 runs
+// under the MMAs of chunk c.  On return the accumulator is complete and visible to tcgen05.ld in every thread.
+__device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int m_tiles, const TcOperand Bm, int n_mma, int kpad,
                                         const float* __restrict__ bias = nullptr, int n_bias = 0) {
   const int tid = threadIdx.x;
   const int nchunk = (kpad + kTKC - 1) / kTKC;
-  const uint32_t idesc = t_idesc(n_mma);
-  const int a_groups = (a_rows + 7) >> 3, n_pieces = (a_groups + ((b_rows + 7) >> 3)) * 32;     // 8 rows x 4 K pieces per group
-  const int a_bytes = m_tiles * kTATile, b_bytes = t_up8(b_rows) * kTKC * 4;
-  const int stage_bytes = 2 * (a_bytes + b_bytes);
+  const int a_bytes = A.box_rows * kTKC * 4, b_bytes = Bm.box_rows * kTKC * 4, hi_bytes = a_bytes + b_bytes;
+  const int stage_bytes = 2 * hi_bytes;
   int nstages = kTRingBytes / stage_bytes;
   nstages = nstages > kTMaxStages ? kTMaxStages : nstages;
-  const int ahead = nstages - 1;                   // chunks in flight beyond the one being multiplied
-
-  auto issue_loads = [&](int c) {
-    const int stage = c % nstages;
-    if (R.pend & (1u << stage)) {                  // the MMAs that read this slot have retired
-      t_mbar_wait(&R.empty[stage], (R.par >> stage) & 1u);
-      R.par ^= 1u << stage; R.pend &= ~(1u << stage);
-    }
-    const int k0 = c * kTKC;
-    const int kw4 = min(kTKC, kpad - k0) >> 2;                         // 16-byte pieces per row in this chunk (2 or 4)
-    const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + 2 * a_bytes;
-    for (int p = tid; p < n_pieces; p += kTT) {
-      const int grp = p >> 5, pc = (p >> 3) & 3, r8 = p & 7;
-      if (pc >= kw4) continue;
-      if (grp < a_groups) {
-        const int row = grp * 8 + r8;
-        if (row < a_rows) t_cp16(sA + (uint32_t)((grp * 4 + pc) * 128 + r8 * 16), tc_piece(A, row, k0 + 4 * pc));
-      } else {
-        const int gb = grp - a_groups, row = gb * 8 + r8;
-        if (row < b_rows) t_cp16(sB + (uint32_t)((gb * 4 + pc) * 128 + r8 * 16), tc_piece(Bm, row, k0 + 4 * pc));
-      }
-    }
-  };
-  // hi = TF32(x) (in place), lo = x - hi, of exactly the pieces this thread copied (its own cp.async groups are complete)
-  auto make_lo = [&](int c) {
-    const int stage = c % nstages;
-    const int k0 = c * kTKC;
-    const int kw4 = min(kTKC, kpad - k0) >> 2;
-    uint8_t* sA = R.base + (size_t)stage * stage_bytes;
-    uint8_t* sB = sA + 2 * a_bytes;
-    for (int p = tid; p < n_pieces; p += kTT) {
-      const int grp = p >> 5, pc = (p >> 3) & 3, r8 = p & 7;
-      if (pc >= kw4) continue;
-      uint8_t* hi; uint8_t* lo;
-      if (grp < a_groups) {
-        if (grp * 8 + r8 >= a_rows) continue;
-        hi = sA + (grp * 4 + pc) * 128 + r8 * 16; lo = hi + a_bytes;
-      } else {
-        const int gb = grp - a_groups;
-        if (gb * 8 + r8 >= b_rows) continue;
-        hi = sB + (gb * 4 + pc) * 128 + r8 * 16; lo = hi + b_bytes;
-      }
-      const float4 x = *reinterpret_cast<const float4*>(hi);
-      const float4 h = make_float4(t_hi(x.x), t_hi(x.y), t_hi(x.z), t_hi(x.w));
-      *reinterpret_cast<float4*>(hi) = h;
-      *reinterpret_cast<float4*>(lo) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-    }
-  };
 
   TC_T0();
-  for (int c = 0; c < ahead; ++c) {                // prologue: `ahead` groups (empty ones past the end keep the count uniform)
-    if (c < nchunk) issue_loads(c);
-    t_cp_commit();
-  }
-  if (bias != nullptr)
-    for (int i = tid; i < n_bias; i += kTT) R.bias_s[i] = bias[i];    // visible after the main loop's barriers
-  for (int c = 0; c < nchunk; ++c) {
-    t_cp_wait_dyn<kTMaxStages - 2>(ahead - 1);     // all but the newest ahead - 1 groups are complete: chunk c has landed
-#if !defined(VAE_TC_EXP) || VAE_TC_EXP != 1
-    make_lo(c);
-#endif
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> tensor-core reads
-    __syncthreads();
-    const int stage = c % nstages;
-    if (tid == 0) {
+  if (tid == 0) {
+    // ===================== feeding thread: TMA producer + MMA issuer
+    const uint32_t idesc = t_idesc(n_mma);
+    auto load = [&](int c) {
+      const int stage = c % nstages;
+      if (R.pend & (1u << stage)) {                // the MMAs that read this slot have retired
+        t_mbar_wait(&R.empty[stage], (R.par >> stage) & 1u);
+        R.par ^= 1u << stage; R.pend &= ~(1u << stage);
+      }
+      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes);
+      t_expect_tx(&R.full[stage], (uint32_t)hi_bytes);
+      t_tma_chunk(sA, A.tm, &R.full[stage], c, A.grouped);
+      t_tma_chunk(sA + a_bytes, Bm.tm, &R.full[stage], c, Bm.grouped);
+    };
+    TC_LAPS();
+    for (int c = 0; c < nstages - 1 && c < nchunk; ++c) load(c);
+    TC_LAP(8);
+    for (int c = 0; c < nchunk; ++c) {
+      const int stage = c % nstages;
+      if (c + nstages - 1 < nchunk) load(c + nstages - 1);            // the slot of chunk c - 1 (its MMAs were queued last iteration)
+      TC_LAP(9);
+      t_mbar_wait(&R.ready[stage], (R.rpar >> stage) & 1u);            // chunk c is split into hi / lo
+      R.rpar ^= 1u << stage;
+      TC_LAP(10);
       t_fence_after();
-      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + 2 * a_bytes;
+      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + a_bytes;
       const int ksteps = min(kTKC, kpad - c * kTKC) >> 3;
       for (int s = 0; s < ksteps; ++s) {
-        const uint64_t dBh = t_desc(sB + s * 256), dBl = t_desc(sB + b_bytes + s * 256);
+        // K = 8 step s: +32 bytes inside the 64-byte rows (row-major) / the next [row][32 B] group block (group-major)
+        const uint32_t ka = (uint32_t)(A.grouped ? s * A.box_rows * 32 : s * 32);
+        const uint32_t kb = (uint32_t)(Bm.grouped ? s * Bm.box_rows * 32 : s * 32);
+        const uint64_t dBh = t_desc(sB + kb, Bm.grouped), dBl = t_desc(sB + hi_bytes + kb, Bm.grouped);
         for (int t = 0; t < m_tiles; ++t) {
-          const uint64_t dAh = t_desc(sA + t * kTATile + s * 256), dAl = t_desc(sA + a_bytes + t * kTATile + s * 256);
+          const uint32_t ta = (uint32_t)(t * 128 * (A.grouped ? 32 : 64));                  // M tile t: 128 rows further
+          const uint64_t dAh = t_desc(sA + ka + ta, A.grouped), dAl = t_desc(sA + hi_bytes + ka + ta, A.grouped);
           const uint32_t d = R.tmem + (uint32_t)(t * 256);
           // The tensor core accumulates FP32 with round-toward-zero.  Single-tile GEMMs (forward, dX: K up to 200)
           // keep the two correction products in their own accumulator (columns 256..) so that the small terms are
@@ -312,26 +292,48 @@ __device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int a_rows
         }
       }
       t_commit(&R.empty[stage]);
+      R.pend |= 1u << stage;
       if (c == nchunk - 1) t_commit(R.accfull);
+      TC_LAP(11);
     }
-    R.pend |= 1u << stage;
-    // refill the slot chunk c - 1 was multiplied from (its MMAs were queued one iteration ago) while chunk c runs
-#if defined(VAE_TC_EXP) && VAE_TC_EXP == 2
-    if (c + ahead < nchunk && R.pend & (1u << ((c + ahead) % nstages))) {
-      const int st = (c + ahead) % nstages;
-      t_mbar_wait(&R.empty[st], (R.par >> st) & 1u); R.par ^= 1u << st; R.pend &= ~(1u << st);
-    }
-#else
-    if (c + ahead < nchunk) issue_loads(c + ahead);
+  } else if (tid >= 32) {
+    // ===================== converter warps: hi = TF32(x) rounded to nearest (in place), lo = x - hi
+    const int ct = tid - 32;
+    if (bias != nullptr)
+      for (int i = ct; i < n_bias; i += kTT - 32) R.bias_s[i] = bias[i];
+    const int n4 = hi_bytes >> 4;
+    for (int c = 0; c < nchunk; ++c) {
+      const int stage = c % nstages;
+#ifdef VAE_TC_PROFILE
+      long long _tl = clock64();
 #endif
-    t_cp_commit();
+      t_mbar_wait(&R.full[stage], (R.fpar >> stage) & 1u);             // the chunk's two boxes have landed
+      R.fpar ^= 1u << stage;
+      if (tid == 32) TC_LAP(12);
+      float4* hi = reinterpret_cast<float4*>(R.base + (size_t)stage * stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(R.base + (size_t)stage * stage_bytes + hi_bytes);
+#pragma unroll 3
+      for (int p = ct; p < n4; p += kTT - 32) {
+        const float4 x = hi[p];
+        // hi rounded to nearest, not the hardware's truncation of a raw operand: with truncation lo >= 0 always and the
+        // dropped Al.Bl term biases every product the same way (measured: loss error 3.9e-6 instead of 2.0e-6)
+        const float4 h = make_float4(t_hi(x.x), t_hi(x.y), t_hi(x.z), t_hi(x.w));
+        hi[p] = h;
+        lo[p] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy smem writes -> tensor-core reads
+      __syncwarp();
+      if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_smem(&R.ready[stage])) : "memory");
+      if (tid == 32) TC_LAP(13);
+    }
   }
   TC_ACC(0);
   t_mbar_wait(R.accfull, R.gemms & 1u);
   TC_ACC(1);
   R.gemms += 1;
-  R.par ^= R.pend; R.pend = 0;                     // every outstanding commit has completed with the accumulator
+  if (tid == 0) { R.par ^= R.pend; R.pend = 0; }   // every outstanding commit has completed with the accumulator
   t_fence_after();
+  __syncthreads();                                 // bias_s is visible; every thread is past the main loop
 }
 
 // End of an epilogue: TMEM reads and global writes of all threads are done before the next GEMM starts.
@@ -364,7 +366,7 @@ __device__ __forceinline__ void tc_pmv_load(const float* P, int pm, TcPmv& x) {
 }
 __device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
                                                const TcHyper& hp) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, half = warp >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, cg = warp >> 2;
   const int ngroups = Ly.Np >> 3;
   for (int t = 0; t < m_tiles; ++t) {
     if (t * 128 + q * 32 > Ly.Kuse) continue;                        // no row of this warp's lane quarter is a parameter
@@ -373,36 +375,27 @@ __device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restric
     // address of column group g: kernel row k -> W + (g K + k) 8 ; bias -> Bv + 8 g
     const float* base = is_b ? ws + Ly.Bv : ws + Ly.W + (size_t)(live ? k : 0) * 8;
     const size_t gstride = is_b ? 8 : (size_t)Ly.K * 8;
-    TcPmv buf[3];
-    if (live) {
-      if (half < ngroups) tc_pmv_load(base + half * gstride, pm, buf[0]);
-      if (half + 2 < ngroups) tc_pmv_load(base + (half + 2) * gstride, pm, buf[1]);
-    }
-    int slot = 0;
-    for (int g = half; g < ngroups; g += 2, slot = slot == 2 ? 0 : slot + 1) {
-      const int pre = slot == 0 ? 2 : slot - 1;                       // slot that becomes free: prefetch group g + 4 into it
-      if (live && g + 4 < ngroups) {
-        const float* pp = base + (g + 4) * gstride;
-        if (pre == 0) tc_pmv_load(pp, pm, buf[0]);
-        else if (pre == 1) tc_pmv_load(pp, pm, buf[1]);
-        else tc_pmv_load(pp, pm, buf[2]);
-      }
+    TcPmv cur, nxt;
+    if (live && cg < ngroups) tc_pmv_load(base + cg * gstride, pm, cur);
+    for (int g = cg; g < ngroups; g += kTCG) {
+      if (live && g + kTCG < ngroups) tc_pmv_load(base + (g + kTCG) * gstride, pm, nxt);      // in flight during the update of g
       float acc[8];
       if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
       else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
-      if (!live) continue;
-      TcPmv x = slot == 0 ? buf[0] : slot == 1 ? buf[1] : buf[2];
-      const int n0 = g * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (n0 + j < Ly.N) x.p[j] = t_adam(x.p[j], x.m[j], x.v[j], acc[j], hp);
-      float* P = const_cast<float*>(base) + g * gstride;
-      t_stg8(P, x.p); t_stg8(P + pm, x.m); t_stg8(P + 2 * pm, x.v);
-      if (is_w) {
+      if (live) {
+        const int n0 = g * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (n0 + j < Ly.N) ws[Ly.WT + (size_t)(n0 + j) * Ly.Kp + k] = x.p[j];
+          if (n0 + j < Ly.N) cur.p[j] = t_adam(cur.p[j], cur.m[j], cur.v[j], acc[j], hp);
+        float* P = const_cast<float*>(base) + g * gstride;
+        t_stg8(P, cur.p); t_stg8(P + pm, cur.m); t_stg8(P + 2 * pm, cur.v);
+        if (is_w) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + j < Ly.N) ws[Ly.WT + (size_t)(n0 + j) * Ly.Kp + k] = cur.p[j];
+        }
       }
+      cur = nxt;
     }
   }
 }
@@ -410,11 +403,11 @@ __device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restric
 // Adam epilogue of dW in the TRANSPOSED orientation: accumulator row = n (tile t, lane r), column = k; column Kuse = bias.
 __device__ __forceinline__ void tc_adam_transposed(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
                                                    int n_cols, const TcHyper& hp) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, half = warp >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, cg = warp >> 2;
   const int ngroups = n_cols >> 3;
   for (int t = 0; t < m_tiles; ++t) {
     const int n = t * 128 + q * 32 + lane;
-    for (int g = half; g < ngroups; g += 2) {
+    for (int g = cg; g < ngroups; g += kTCG) {
       float acc[8];
       if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
       else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
@@ -434,20 +427,20 @@ __device__ __forceinline__ void tc_adam_transposed(const TcRing& R, float* __res
 }
 
 // dW of one layer (+ Adam).  Orientation: rows = the larger of (Kuse + 1, N) so the small dimension is the MMA N.
-__device__ __forceinline__ void tc_dw(TcRing& R, float* __restrict__ ws, const TcLayer& Ly, const float* gT, int BP, int pm,
+__device__ __forceinline__ void tc_dw(TcRing& R, float* __restrict__ ws, const TcLayer& Ly, const CUtensorMap* lm, int BP, int pm,
                                       const TcHyper& hp) {
-  const float* XT = ws + Ly.in_T;
+  const int xrows = t_up8(Ly.Kuse + 1);            // X^T rows incl. the ones row (box rows of the TM_INT map)
   if (Ly.Kuse + 1 >= Ly.N) {                       // normal: D[k][n]
-    const int rows = Ly.Kuse + 1, tiles = (rows + 127) >> 7;
-    tc_gemm(R, TcOperand{XT, BP, 0}, rows, tiles, TcOperand{gT, BP, 0}, Ly.N, Ly.Np, BP);
+    const int tiles = (Ly.Kuse + 1 + 127) >> 7;
+    tc_gemm(R, TcOperand{lm + TM_INT, 0, xrows}, tiles, TcOperand{lm + TM_GT, 0, Ly.Np}, Ly.Np, BP);
     TC_T0();
     tc_adam_normal(R, ws, Ly, pm, tiles, hp);
     TC_ACC(2);
   } else {                                          // transposed: D[n][k]
-    const int cols = t_up8(Ly.Kuse + 1), tiles = (Ly.N + 127) >> 7;
-    tc_gemm(R, TcOperand{gT, BP, 0}, Ly.N, tiles, TcOperand{XT, BP, 0}, Ly.Kuse + 1, cols, BP);
+    const int tiles = (Ly.N + 127) >> 7;
+    tc_gemm(R, TcOperand{lm + TM_GT, 0, Ly.Np}, tiles, TcOperand{lm + TM_INT, 0, xrows}, xrows, BP);
     TC_T0();
-    tc_adam_transposed(R, ws, Ly, pm, tiles, cols, hp);
+    tc_adam_transposed(R, ws, Ly, pm, tiles, xrows, hp);
     TC_ACC(3);
   }
   tc_epilogue_done();
@@ -456,22 +449,24 @@ __device__ __forceinline__ void tc_dw(TcRing& R, float* __restrict__ ws, const T
 __global__ void __launch_bounds__(kTT, 1)
 fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
   extern __shared__ uint8_t tc_raw[];
-  __shared__ TcJobDev J;
-  __shared__ __align__(8) uint64_t bars[kTMaxStages + 1];
+  __shared__ TcJobDev J;                                            // (the tensor maps at its end are not copied)
+  __shared__ __align__(8) uint64_t bars[3 * kTMaxStages + 1];
   __shared__ float bias_s[kTMaxN];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[kTT / 32];
-  __shared__ float lvred[kTT / 32][64];
+  __shared__ float red[kTW];
+  __shared__ float lvred[kTW][64];
   __shared__ uint32_t keys[8];
   __shared__ float sl_s[64], scal_s[4];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, half = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cg = warp >> 2;
+  const CUtensorMap* gmaps = jobs[blockIdx.x].maps;                 // TMA reads the maps from the job table itself
   {
     const int* src = reinterpret_cast<const int*>(jobs + blockIdx.x);
     int* dst = reinterpret_cast<int*>(&J);
-    for (int i = tid; i < (int)(sizeof(TcJobDev) / 4); i += kTT) dst[i] = src[i];
+    for (int i = tid; i < (int)(offsetof(TcJobDev, maps) / 4); i += kTT) dst[i] = src[i];
   }
   if (tid == 0) {
-    for (int i = 0; i <= kTMaxStages; ++i) t_mbar_init(&bars[i], 1);
+    for (int i = 0; i <= 3 * kTMaxStages; ++i)
+      t_mbar_init(&bars[i], (i >= kTMaxStages && i < 2 * kTMaxStages) ? kTW - 1 : 1);       // ready[]: one arrive per converter warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -483,8 +478,9 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
   t_fence_after();
   TcRing R;
   R.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
-  R.empty = &bars[0]; R.accfull = &bars[kTMaxStages]; R.bias_s = bias_s;
-  R.par = 0; R.pend = 0; R.gemms = 0; R.tmem = tmem_base_s;
+  R.full = &bars[0]; R.ready = &bars[kTMaxStages]; R.empty = &bars[2 * kTMaxStages]; R.accfull = &bars[3 * kTMaxStages];
+  R.bias_s = bias_s;
+  R.fpar = 0; R.rpar = 0; R.par = 0; R.pend = 0; R.gemms = 0; R.tmem = tmem_base_s;
 
   const int B = J.B, BP = J.BP, D = J.D, L = J.L, DR = J.DR, G = J.G, LD = J.LD, Lp = J.Lp;
   float* __restrict__ ws = J.ws;
@@ -613,12 +609,13 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
       for (int i = 0; i < nl; ++i) {
         const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
         const int kpad = i == 0 ? t_up8(Ly.Kuse) : Ly.Kp;
-        tc_gemm(R, TcOperand{ws + Ly.in_bm, BP, 1}, BP, 1, TcOperand{ws + Ly.WT, Ly.Kp, 0}, Ly.N, Ly.Np, kpad, ws + Ly.Bv, Ly.N);
+        const CUtensorMap* lm = gmaps + (net * kTMaxL + i) * TM_PER_LAYER;
+        tc_gemm(R, TcOperand{lm + TM_INBM, 1, 128}, 1, TcOperand{lm + TM_WT, 0, Ly.Np}, Ly.Np, kpad, ws + Ly.Bv, Ly.N);
         TC_T0();
         const float* bias = R.bias_s;
         const bool last = i == nl - 1;
-        uint64_t mlo = 0, mhi = 0;                       // relu'(output) bytes of this thread's column groups (hidden layers)
-        for (int g = half; g < (Ly.Np >> 3); g += 2) {
+        uint64_t mbits = 0;                              // relu'(output) bytes of this thread's column groups (hidden layers)
+        for (int g = cg; g < (Ly.Np >> 3); g += kTCG) {
           float acc[8];
           t_ld8_sum(trow + (uint32_t)(g * 8), acc);
           if (row >= BP) continue;
@@ -636,8 +633,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
             uint64_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) bits |= (uint64_t)(y[j] > 0.f ? 1u : 0u) << j;
-            const int idx = g >> 1;
-            if (idx < 8) mlo |= bits << (idx * 8); else mhi |= bits << ((idx - 8) * 8);
+            mbits |= bits << ((g / kTCG) * 8);
           } else if (net == 0) {                         // mu; zs = mu + exp(lv/2) z1 (networks.py:67-74)
             const TcLayer& D0 = J.dec[0];
             float mu[8], zs[8];
@@ -676,9 +672,8 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
               if (n0 + j < D) ws[J.ws_gT[0] + (size_t)(n0 + j) * BP + row] = gq[j];
           }
         }
-        if (!last && row < BP)                           // [BP][2 halves][16 bytes]: read back by the same (row, half) thread
-          reinterpret_cast<uint4*>(ws + Ly.out_mask)[row * 2 + half] =
-              make_uint4((uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32));
+        if (!last && row < BP)                           // [BP][kTCG][8 bytes]: read back by the same (row, cg) thread
+          reinterpret_cast<uint2*>(ws + Ly.out_mask)[row * kTCG + cg] = make_uint2((uint32_t)mbits, (uint32_t)(mbits >> 32));
         tc_epilogue_done();
         TC_ACC(4);
       }
@@ -707,22 +702,21 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
       const int nl = net ? nd : ne;
       for (int i = nl - 1; i >= 0; --i) {
         const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
-        const float* gbm = ws + J.ws_gbm[cur];
-        const float* gT = ws + J.ws_gT[cur];
         const bool need_dx = !(net == 0 && i == 0);
         if (need_dx) {
           // dX[b][k] = sum_n dY[b][n] W[k][n] with the OLD weights (Adam of this layer runs after)
           const bool latent = net == 1 && i == 0;       // dzs: -> d lv partials, dmu = dzs + mu / B
-          uint64_t mlo = 0, mhi = 0;                     // relu'(layer input) bytes of this thread's (row, half) column groups
+          uint64_t mbits = 0;                            // relu'(layer input) bytes of this thread's (row, cg) column groups
           if (!latent && row < BP) {
-            const uint4 mk = reinterpret_cast<const uint4*>(ws + Ly.in_mask)[row * 2 + half];
-            mlo = (uint64_t)mk.x | ((uint64_t)mk.y << 32); mhi = (uint64_t)mk.z | ((uint64_t)mk.w << 32);
+            const uint2 mk = reinterpret_cast<const uint2*>(ws + Ly.in_mask)[row * kTCG + cg];
+            mbits = (uint64_t)mk.x | ((uint64_t)mk.y << 32);
           }
-          tc_gemm(R, TcOperand{gbm, BP, 1}, BP, 1, TcOperand{ws + Ly.W, Ly.K, 1}, Ly.K, Ly.Kp, Ly.Np);
+          const CUtensorMap* lm = gmaps + (net * kTMaxL + i) * TM_PER_LAYER;
+          tc_gemm(R, TcOperand{gmaps + 2 * kTMaxL * TM_PER_LAYER + cur, 1, 128}, 1, TcOperand{lm + TM_W8, 1, Ly.Kp}, Ly.Kp, Ly.Np);
           TC_T0();
           float* obm = ws + J.ws_gbm[cur ^ 1];
           float* oT = ws + J.ws_gT[cur ^ 1];
-          for (int g = half; g < (Ly.Kp >> 3); g += 2) {
+          for (int g = cg; g < (Ly.Kp >> 3); g += kTCG) {
             float acc[8];
             t_ld8_sum(trow + (uint32_t)(g * 8), acc);
             const int k0 = g * 8;
@@ -730,8 +724,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
             const size_t gofs = ((size_t)g * BP + (row < BP ? row : 0)) * 8;
             float o[8];
             if (!latent) {
-              const int idx = g >> 1;
-              const uint32_t bits = (uint32_t)((idx < 8 ? mlo >> (idx * 8) : mhi >> ((idx - 8) * 8)) & 0xFFu);
+              const uint32_t bits = (uint32_t)(mbits >> ((g / kTCG) * 8)) & 0xFFu;
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = (vrow && ((bits >> j) & 1u)) ? acc[j] : 0.f;
             } else {
@@ -760,7 +753,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
           tc_epilogue_done();
           TC_ACC(5);
           if (latent && tid < L) {          // g_lv[l] = sum_b dzs z1 * 0.5 s_l - 0.5 (1 - e^lv_l)
-            const int gsel = (tid >> 3) & 1;  // column group g was drained by the warps with half == g & 1
+            const int gsel = (tid >> 3) % kTCG;   // column group g was drained by the four warps with cg == g % kTCG
             float a = 0.f;
             for (int w = 0; w < 4; ++w) a += lvred[4 * gsel + w][tid];
             const float lv = J.params[J.off_lv + tid];
@@ -769,7 +762,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
             J.adam_m[J.off_lv + tid] = m; J.adam_v[J.off_lv + tid] = v;
           }
         }
-        tc_dw(R, ws, Ly, gT, BP, pm, hp);
+        tc_dw(R, ws, Ly, gmaps + (net * kTMaxL + i) * TM_PER_LAYER, BP, pm, hp);
         cur ^= need_dx ? 1 : 0;
       }
     }
@@ -811,8 +804,50 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Workspace layout (floats).  Every offset is a multiple of 4 floats (16-byte cp.async); every row stride a
-// multiple of 8.  The caller zero-fills the workspace once (padding rows / columns are never written).
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = nullptr;      // idempotent lookup of a driver entry point
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TcEncodeFn>(p);
+  }
+  return fn;
+}
+// Operand maps (out-of-range rows / K are zero-filled by TMA):
+//   row-major [rows][ld]:        2-D {kfloats, rows}, row stride ld * 4 bytes;  box {16, box_rows}, SWIZZLE_64B
+//   group-major [k / 8][ld][8]:  3-D {8, rows, kfloats / 8}, strides {32, ld * 32} bytes;  box {8, box_rows, 2}, SWIZZLE_32B
+static int tc_make_map(CUtensorMap* tm, const float* ptr, int grouped, int rows, int kfloats, int ld, int box_rows) {
+  TcEncodeFn enc = tc_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VAE_ERR_CUDA; }
+  CUresult r;
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (!grouped) {
+    cuuint64_t gdim[2] = {(cuuint64_t)kfloats, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(kfloats / 8)};
+    cuuint64_t gstr[2] = {32, (cuuint64_t)ld * 32};
+    cuuint32_t box[3] = {8, (cuuint32_t)box_rows, 2};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d; grouped %d rows %d k %d ld %d box %d)", (int)r, grouped, rows, kfloats, ld, box_rows);
+    return VAE_ERR_CUDA;
+  }
+  return 0;
+}
+
+// Workspace layout (floats).  Every offset is a multiple of 8 floats; every row stride a multiple of 8.  The caller
+// zero-fills the workspace once (padding rows / columns are never written).
 static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
   Layout Lo;
   if (make_layout(&j.desc, &Lo)) return 0;
@@ -866,7 +901,33 @@ static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
   }
   J.ws_z = take((size_t)BP * (L + D) + 8); J.ws_gn = take((size_t)BP * G + 8); J.ws_mu = take((size_t)BP * J.Lp);
   for (int b = 0; b < 2; ++b) { J.ws_gbm[b] = take((size_t)BP * maxw); J.ws_gT[b] = take((size_t)(maxw + 8) * BP); }
+  // which gradient buffer holds each layer's dY: the backward pass walks dec[nd-1] .. dec[0], enc[ne-1] .. enc[0]
+  // and flips after every layer that produces a dX
+  {
+    int cur = 0;
+    for (int net = 1; net >= 0; --net)
+      for (int i = (net ? Lo.n_dec : Lo.n_enc) - 1; i >= 0; --i) {
+        TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+        Ly.gcur = cur;
+        if (!(net == 0 && i == 0)) cur ^= 1;
+      }
+  }
   if (o) {
+    const float* wsb = (const float*)j.workspace;
+    for (int net = 0; net < 2; ++net)
+      for (int i = 0; i < (net ? Lo.n_dec : Lo.n_enc); ++i) {
+        const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
+        CUtensorMap* lm = J.maps + (net * kTMaxL + i) * TM_PER_LAYER;
+        const int xrows = t_up8(Ly.Kuse + 1);
+        if (tc_make_map(lm + TM_WT, wsb + Ly.WT, 0, Ly.Np, Ly.Kp, Ly.Kp, Ly.Np) ||                 // B of the forward GEMM
+            tc_make_map(lm + TM_W8, wsb + Ly.W, 1, Ly.K, Ly.Np, Ly.K, Ly.Kp) ||                   // B of dX: rows k, K = n
+            tc_make_map(lm + TM_INBM, wsb + Ly.in_bm, 1, BP, Ly.Kp, BP, 128) ||                   // A of the forward GEMM
+            tc_make_map(lm + TM_INT, wsb + Ly.in_T, 0, xrows, BP, BP, xrows) ||                   // X^T (+ ones row) of dW
+            tc_make_map(lm + TM_GT, wsb + J.ws_gT[Ly.gcur], 0, Ly.Np, BP, BP, Ly.Np))             // dY^T of dW
+          return 0;
+      }
+    for (int b = 0; b < 2; ++b)
+      if (tc_make_map(J.maps + 2 * kTMaxL * TM_PER_LAYER + b, wsb + J.ws_gbm[b], 1, BP, maxw, BP, 128)) return 0;   // A of dX
     *o = J;
     o->params = j.params; o->adam_m = j.adam_m; o->adam_v = j.adam_v; o->step = j.step;
     o->model_key = j.model_key; o->dataset_key = j.dataset_key; o->A = j.A; o->loss_out = j.loss_out;
