@@ -147,6 +147,21 @@ int vae_loss_and_grad(const VaeDesc* desc, const float* params, const float* d_x
                       const float* d_z, int32_t rows, int32_t grad_scale_rows,
                       float* d_loss, float* d_grad, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* The same gradient with per-segment completion events, for overlapping the data-parallel allreduce with the
+ * backward pass ("bucketed per layer and overlapped with backward").  vae_grad_segments lists the
+ * flat-gradient ranges in the order the backward pass completes them (decoder layers last -> first, the latent
+ * block epsilon_p/epsilon, encoder layers last -> first; one segment for two-decoder models); it returns the
+ * count (out may be NULL).  ready_events: one cudaEvent_t per segment, recorded on `stream` as soon as that range
+ * of d_grad is final.  vae_adam_update_range applies flax Adam (networks.py:100) to [begin, end) only and does
+ * not advance the step counter; vae_adam_step_increment advances it once all ranges are done. */
+typedef struct VaeGradSegment { int64_t begin, end; } VaeGradSegment;
+int32_t vae_grad_segments(const VaeDesc* desc, VaeGradSegment* out, int32_t max_out);
+int vae_loss_and_grad_events(const VaeDesc* desc, const float* params, const float* d_x, const float* d_z,
+                             int32_t rows, int32_t grad_scale_rows, float* d_loss, float* d_grad,
+                             void* workspace, size_t workspace_bytes, void* const* ready_events, void* stream);
+int vae_adam_update_range(const VaeDesc* desc, float* params, float* adam_m, float* adam_v, const int32_t* d_step,
+                          const float* d_grad, int64_t begin, int64_t end, void* stream);
+int vae_adam_step_increment(int32_t* d_step, void* stream);
 /* flax.optim.Adam.apply_gradient (networks.py:100) on a flat gradient. */
 int vae_adam_update(const VaeDesc* desc, float* params, float* adam_m, float* adam_v,
                     int32_t* d_step, const float* d_grad, void* stream);

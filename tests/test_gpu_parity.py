@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star):
     (checked against the oracle's float64 shadow where the oracle's own float32
     rounding would otherwise dominate).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -608,6 +610,46 @@ def test_data_parallel_emulated_ranks_match_single(ops, lib):
     assert np.max(np.abs(got - ref) / np.abs(ref)) <= REL_STEP
     np.testing.assert_array_equal(model.key.cpu().numpy(), tr.key)
     np.testing.assert_array_equal(model.dkey.cpu().numpy(), ods_.key)
+
+
+def test_data_parallel_overlapped_exchange_equals_plain(ops, lib):
+    """The bucketed exchange (per-segment events from vae_loss_and_grad_events, side-stream allreduce + ranged Adam)
+    is the same arithmetic as gradient -> one allreduce -> Adam: bit-identical state and losses at world 1, for a
+    model on the FFMA GEMM route and one on the tcgen05 route; the segments tile the flat gradient exactly."""
+    from vae_training_b200 import dp
+    from vae_training_b200.packed import RunSpec
+    for hid, batch, D in (([32, 24], 60, 8), ([256, 320], 1024, 64)):
+        spec = RunSpec("sphere", D - 3, 3, 4, encoder_layer_sizes=hid, layer_sizes=hid[::-1], batch_size=batch,
+                       learning_rate=1e-4, epsilon=-2.0, tunable_decoder_var=True)
+        d = vs.VaeDesc(batch, D, 4, hid, hid[::-1], epsilon0=-2.0, lr=1e-4)
+        flat = vs.init_params(d, 3)
+        mk, dk = jr.PRNGKey(21), jr.PRNGKey(22)
+        a = dp.DataParallelVAE(spec, flat, mk, dk, rank=0, world=1, overlap=False)
+        b = dp.DataParallelVAE(spec, flat, mk, dk, rank=0, world=1, overlap=True)
+        assert b.overlap and len(b.segments) == 2 * (len(hid) + 1) + 1
+        covered = sorted(b.segments)
+        assert covered[0][0] == 0 and covered[-1][1] == d.n_params
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+        la = torch.cat([a.train_step().clone() for _ in range(6)])
+        lb = torch.cat([b.train_step().clone() for _ in range(6)])
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb)
+        for k in ("params", "adam_m", "adam_v", "step", "key", "dkey"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (run with gpurun --gpus 2)")
+def test_data_parallel_two_gpus_match_one(tmp_path):
+    """scripts/dp_check.py under torchrun on 2 GPUs: the N-rank loss sequence within 1e-5 of the single-GPU run,
+    replicas bit-identical (NCCL allreduce of the bucketed gradient)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "scripts", "dp_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "DP CHECK OK" in out.stdout
 
 
 # ------------------------------------------------ fused cluster kernel (hidden-layer models)

@@ -72,6 +72,11 @@ _PROTOTYPES = {
     "vae_loss_and_grad": (C.c_int, [C.POINTER(VaeDesc), _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                     C.c_size_t, _P]),
     "vae_adam_update": (C.c_int, [C.POINTER(VaeDesc), _P, _P, _P, _P, _P, _P]),
+    "vae_grad_segments": (C.c_int32, [C.POINTER(VaeDesc), _P, C.c_int32]),
+    "vae_loss_and_grad_events": (C.c_int, [C.POINTER(VaeDesc), _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
+                                           C.c_size_t, _P, _P]),
+    "vae_adam_update_range": (C.c_int, [C.POINTER(VaeDesc), _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "vae_adam_step_increment": (C.c_int, [_P, _P]),
     "vae_loss": (C.c_int, [C.POINTER(VaeDesc), _P, _P, _P, C.c_int32, _P, _P, C.c_size_t, _P]),
     "vae_sample": (C.c_int, [C.POINTER(VaeDesc), _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "vae_train_fused_supported": (C.c_int, [C.POINTER(VaeTrainJob)]),

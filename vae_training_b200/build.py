@@ -23,7 +23,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2",
-] + [f"-D{k}={os.environ[k]}" for k in ("VAE_SMALL_MAXB", "VAE_SMALL_GM_MODELS") if os.environ.get(k)]
+] + [f"-D{k}={os.environ[k]}" for k in ("VAE_SMALL_MAXB", "VAE_SMALL_GM_MODELS") if os.environ.get(k)] \
+  + [f"-D{d}" for d in os.environ.get("VAE_B200_DEFINES", "").split() if d]      # e.g. VAE_TC_PROFILE (A/B + profiling builds)
 
 
 def find_nvcc() -> str:

@@ -396,9 +396,13 @@ static int mlp_forward(cudaStream_t s, const float* params, const int* sizes, in
 static int mlp_backward(cudaStream_t s, const float* params, float* grad, const int* sizes, int n_layers,
                         const int64_t* w_off, const int64_t* b_off, const float* input,
                         float* const* acts, int rows, const float* dout, float* ga, float* gb,
-                        float* d_in, bool need_dx, bool acc_dx, const Workspace* tcw = nullptr) {
+                        float* d_in, bool need_dx, bool acc_dx, const Workspace* tcw = nullptr,
+                        void* const* ready = nullptr) {
+  // ready (may be null): one cudaEvent_t per layer, recorded on `s` once that layer's kernel + bias gradient is final
+  // (ready[0] = the LAST layer, the first one the backward pass finishes)
   const float* d = dout;
   for (int i = n_layers - 1; i >= 0; --i) {
+    if (ready && i < n_layers - 1) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[n_layers - 2 - i], s));   // layer i + 1 is complete
     const int in = sizes[i], out = sizes[i + 1];
     const float* h_in = i == 0 ? input : acts[i - 1];
     if (tcw && tcw->tc && !acc_dx) {
@@ -444,6 +448,7 @@ static int mlp_backward(cudaStream_t s, const float* params, float* grad, const 
       if (rc) return rc;
     }
   }
+  if (ready) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[n_layers - 1], s));      // layer 0 is complete
   return 0;
 }
 
@@ -451,7 +456,8 @@ enum Mode { MODE_GRAD, MODE_LOSS, MODE_SAMPLE };
 
 static int run(const VaeDesc* desc, const float* params, const float* d_x, const float* d_z, int rows,
                int scale_rows, Mode mode, const float* d_cur_eps, float* d_out, int n_out_vals,
-               float* d_grad, float* d_xhat, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+               float* d_grad, float* d_xhat, void* workspace, size_t workspace_bytes, cudaStream_t s,
+               void* const* ready = nullptr) {
   Layout L;
   int rc = make_layout(desc, &L);
   if (rc) return rc;
@@ -507,8 +513,11 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   if (mode == MODE_LOSS) return 0;
 
   // backward: decoder(s) -> dzs
+  // gradient segments in completion order (vae_grad_segments): decoder layers last -> first, the latent block
+  // (epsilon_p, epsilon), encoder layers last -> first.  Two-decoder (sigmoid) models report everything at the end.
+  const bool seg_events = ready != nullptr && !desc->sig_decoder;
   rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, w.dec_act, rows,
-                    w.dxhat, w.ga, w.gb, w.dzs, true, false, &w);
+                    w.dxhat, w.ga, w.gb, w.dzs, true, false, &w, seg_events ? ready : nullptr);
   if (rc) return rc;
   if (desc->sig_decoder) {
     rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.sig_w, L.sig_b, w.zs, w.sig_act, rows,
@@ -519,9 +528,31 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   if (rc) return rc;
   latent_grad_kernel<<<g_lat, 256, 0, s>>>(w.dzs, mu, lv, rows, Ld, inv_bs, grad + L.off_eps_p);
   VAE_LAUNCH_OK("latent_grad_kernel");
+  if (seg_events) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[L.n_dec], s));
   rc = mlp_backward(s, params, grad, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, w.enc_act, rows,
-                    w.dzs, w.ga, w.gb, nullptr, false, false, &w);
-  return rc;
+                    w.dzs, w.ga, w.gb, nullptr, false, false, &w, seg_events ? ready + L.n_dec + 1 : nullptr);
+  if (rc) return rc;
+  if (ready && !seg_events) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[0], s));
+  return 0;
+}
+
+// Flat-gradient segments in the order the backward pass completes them.
+static int grad_segments(const VaeDesc* desc, VaeGradSegment* out, int max_out) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (desc->sig_decoder) {
+    if (out && max_out >= 1) { out[0].begin = 0; out[0].end = L.n_params; }
+    return 1;
+  }
+  const int n = L.n_dec + 1 + L.n_enc;
+  if (!out) return n;
+  VAE_REQUIRE(max_out >= n, "vae_grad_segments: room for %d segments is needed", n);
+  int k = 0;
+  for (int i = L.n_dec - 1; i >= 0; --i, ++k) { out[k].begin = L.dec_w[i]; out[k].end = L.dec_b[i] + L.dec_sizes[i + 1]; }
+  out[k].begin = L.off_eps_p; out[k].end = L.n_params; ++k;
+  for (int i = L.n_enc - 1; i >= 0; --i, ++k) { out[k].begin = L.enc_w[i]; out[k].end = L.enc_b[i] + L.enc_sizes[i + 1]; }
+  return n;
 }
 
 }  // namespace vae
@@ -542,6 +573,41 @@ int vae_loss_and_grad(const VaeDesc* desc, const float* params, const float* d_x
   VAE_REQUIRE(d_loss && d_grad, "vae_loss_and_grad: output pointer is NULL");
   return vae::run(desc, params, d_x, d_z, rows, grad_scale_rows, vae::MODE_GRAD, nullptr, d_loss, 1,
                   d_grad, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int32_t vae_grad_segments(const VaeDesc* desc, VaeGradSegment* out, int32_t max_out) {
+  return vae::grad_segments(desc, out, max_out);
+}
+
+int vae_loss_and_grad_events(const VaeDesc* desc, const float* params, const float* d_x, const float* d_z,
+                             int32_t rows, int32_t grad_scale_rows, float* d_loss, float* d_grad,
+                             void* workspace, size_t workspace_bytes, void* const* ready_events, void* stream) {
+  VAE_REQUIRE(d_loss && d_grad && ready_events, "vae_loss_and_grad_events: NULL pointer");
+  return vae::run(desc, params, d_x, d_z, rows, grad_scale_rows, vae::MODE_GRAD, nullptr, d_loss, 1,
+                  d_grad, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, ready_events);
+}
+
+int vae_adam_update_range(const VaeDesc* desc, float* params, float* adam_m, float* adam_v, const int32_t* d_step,
+                          const float* d_grad, int64_t begin, int64_t end, void* stream) {
+  vae::Layout L;
+  int rc = vae::make_layout(desc, &L);
+  if (rc) return rc;
+  VAE_REQUIRE(params && adam_m && adam_v && d_step && d_grad, "vae_adam_update_range: NULL pointer");
+  VAE_REQUIRE(0 <= begin && begin <= end && end <= L.n_params, "vae_adam_update_range: bad range");
+  if (begin == end) return 0;
+  int64_t blocks = (end - begin + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  vae::adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params + begin, adam_m + begin, adam_v + begin, d_grad + begin,
+                                                                  d_step, end - begin, vae::make_adam_hyper(desc));
+  VAE_LAUNCH_OK("adam_kernel");
+  return 0;
+}
+
+int vae_adam_step_increment(int32_t* d_step, void* stream) {
+  VAE_REQUIRE(d_step, "vae_adam_step_increment: NULL pointer");
+  vae::step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step);
+  VAE_LAUNCH_OK("step_inc_kernel");
+  return 0;
 }
 
 int vae_adam_update(const VaeDesc* desc, float* params, float* adam_m, float* adam_v, int32_t* d_step,

@@ -55,7 +55,7 @@ class DataParallelVAE:
     same update); only the batch rows differ."""
 
     def __init__(self, spec: RunSpec, params: np.ndarray, model_key, dataset_key, A=None, group=None,
-                 device="cuda", rank: Optional[int] = None, world: Optional[int] = None):
+                 device="cuda", rank: Optional[int] = None, world: Optional[int] = None, overlap: bool = True):
         self.spec = spec
         self.group = group
         self.device = device
@@ -84,6 +84,17 @@ class DataParallelVAE:
         self.A = None if A is None else torch.from_numpy(np.asarray(A, np.float32).copy()).to(device)
         self.gbuf = torch.zeros(n + 1, dtype=torch.float32, device=device)      # [gradient | loss]
         self.ws = ops.Workspace(device)
+        # Overlapped exchange: the backward pass records one event per gradient segment (a layer's
+        # kernel + bias, in completion order); a side stream allreduces each segment as it lands and runs Adam on
+        # it, while the main stream is still in the earlier layers' backward GEMMs.
+        self.segments = ops.grad_segments(self.desc)
+        self.overlap = overlap and torch.cuda.is_available() and str(device).startswith("cuda")
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream(device=device)
+            self.events = [torch.cuda.Event() for _ in self.segments]
+            for e in self.events:
+                e.record()                 # torch creates the cudaEvent lazily: make the handles exist
+            self.done = torch.cuda.Event()
 
     def draw(self):
         """This rank's rows of the step's dataset batch and eps (model.py:221, vae.py:125-126)."""
@@ -97,6 +108,8 @@ class DataParallelVAE:
 
     def train_step(self) -> torch.Tensor:
         """One global step; returns the global loss (device scalar view, valid until the next step)."""
+        if self.overlap and self.rows > 0:
+            return self._train_step_overlapped()
         x, z = self.draw()
         grad, loss = self.gbuf[:self.n], self.gbuf[self.n:]
         if self.rows > 0:
@@ -106,4 +119,27 @@ class DataParallelVAE:
         if self.collective:
             allreduce_sum(self.gbuf, self.group)          # the exchange step
         ops.adam_update(self.desc, self.params, self.adam_m, self.adam_v, self.step, grad)
+        return loss
+
+    def _train_step_overlapped(self) -> torch.Tensor:
+        """The same step with the exchange bucketed per gradient segment and overlapped with the backward pass:
+        segment k is allreduced (NCCL, side stream) and Adam-updated as soon as its event fires, while the main
+        stream computes the gradients of the layers below it.  Summation order inside a segment is NCCL's, exactly
+        as in the single-allreduce form; parameters a later GEMM of this step still reads are never touched early
+        (a layer's dX is enqueued before its segment's event)."""
+        main = torch.cuda.current_stream()
+        x, z = self.draw()
+        grad, loss = self.gbuf[:self.n], self.gbuf[self.n:]
+        ops.loss_and_grad_events(self.desc, self.params, x, z, self.rows, self.B, loss, grad, self.ws, self.events)
+        with torch.cuda.stream(self.comm_stream):
+            for (b, e), ev in zip(self.segments, self.events):
+                self.comm_stream.wait_event(ev)
+                if self.collective:
+                    allreduce_sum(self.gbuf[b:e], self.group)
+                ops.adam_update_range(self.desc, self.params, self.adam_m, self.adam_v, self.step, grad, b, e)
+            if self.collective:
+                allreduce_sum(loss, self.group)
+            ops.adam_step_increment(self.step)
+            self.done.record(self.comm_stream)
+        main.wait_event(self.done)                         # the next step reads the updated parameters
         return loss

@@ -164,6 +164,39 @@ def adam_update(desc: VaeDesc, params, adam_m, adam_v, step, grad):
                                       _stream()), "vae_adam_update")
 
 
+def grad_segments(desc: VaeDesc):
+    """[(begin, end)] ranges of the flat gradient in the order the backward pass completes them."""
+    lib = _lib.load()
+    n = int(lib.vae_grad_segments(C.byref(desc), None, 0))
+    if n < 0:
+        check(n, "vae_grad_segments")
+    buf = (C.c_int64 * (2 * n))()
+    check(min(0, int(lib.vae_grad_segments(C.byref(desc), buf, n))), "vae_grad_segments")
+    return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n)]
+
+
+def loss_and_grad_events(desc: VaeDesc, params, x, z, rows: int, grad_scale_rows: int, loss, grad, ws: Workspace, events):
+    """vae_loss_and_grad_events: `events` = one recorded-at-least-once torch.cuda.Event per gradient segment."""
+    p, n = ws.get(desc, rows)
+    arr = (C.c_void_p * len(events))(*[C.c_void_p(e.cuda_event) for e in events])
+    check(_lib.load().vae_loss_and_grad_events(C.byref(desc), _ptr(params, torch.float32, "params"),
+                                               _ptr(x, torch.float32, "x"), _ptr(z, torch.float32, "z"), rows,
+                                               grad_scale_rows, _ptr(loss, torch.float32, "loss"),
+                                               _ptr(grad, torch.float32, "grad"), p, n, arr, _stream()),
+          "vae_loss_and_grad_events")
+
+
+def adam_update_range(desc: VaeDesc, params, adam_m, adam_v, step, grad, begin: int, end: int):
+    check(_lib.load().vae_adam_update_range(C.byref(desc), _ptr(params, torch.float32, "params"),
+                                            _ptr(adam_m, torch.float32, "adam_m"), _ptr(adam_v, torch.float32, "adam_v"),
+                                            _ptr(step, torch.int32, "step"), _ptr(grad, torch.float32, "grad"),
+                                            int(begin), int(end), _stream()), "vae_adam_update_range")
+
+
+def adam_step_increment(step):
+    check(_lib.load().vae_adam_step_increment(_ptr(step, torch.int32, "step"), _stream()), "vae_adam_step_increment")
+
+
 def vae_loss(desc: VaeDesc, params, x, z, rows: int, ws: Workspace) -> torch.Tensor:
     """VAE.loss (networks.py:103-113): float32[3] = loss, dkl.mean, mse.mean."""
     out = torch.empty((3,), dtype=torch.float32, device=params.device)
