@@ -159,6 +159,9 @@ STEP_CASES = {
     "wide_batch": vs.VaeDesc(1000, 16, 8, [64, 48], [48, 64], epsilon0=-2.0),
     # rows >= 1024, width >= 256, all dims % 4 == 0: Dense layers go through the tcgen05 3xTF32 GEMM
     "tc_route": vs.VaeDesc(1024, 64, 16, [256, 320], [256, 256], epsilon0=-2.0),
+    # a scaled-down BASELINE configs[4] model: width 1024 and K = 4096 contractions (encoder layer 0 forward, the
+    # last decoder layer's dX), i.e. the two-level accumulation of gemm_tc.cu over 16 chunks inside a full step
+    "cfg5_small": vs.VaeDesc(1024, 4096, 16, [1024], [1024], epsilon0=-2.0),
 }
 
 
@@ -205,19 +208,20 @@ def test_train_steps_vs_oracle(ops, lib, name):
     ws = ops.Workspace()
     of, om, ov, ostep = flat.astype(np.float64), np.zeros(d.n_params), np.zeros(d.n_params), 0
     L = d.latent_dim
-    for it in range(20):
+    n_it = 10 if d.n_params > 1_000_000 else 20            # the float64 oracle of cfg5_small costs ~1 s per step
+    for it in range(n_it):
         _, x, z = make_inputs(d, seed=100 + it)
         ops.train_step(cd, P, M, V, step, dev(x), dev(z), loss, ws)
         of, om, ov, ostep, ol = vs.train_step(d, of, om, ov, ostep, x, z[:, :L], z[:, L:], dtype=np.float64)
         assert abs(float(loss) - ol) <= REL_STEP * abs(ol), f"step {it}"
-    assert int(step) == 20
+    assert int(step) == n_it
     # hidden relu layers fed with white-noise inputs leave many coordinates with gradients at
     # rounding-noise level (see assert_params_close); the well-conditioned variant below
     # requires every coordinate
-    assert_params_close(P.cpu().numpy(), of, 20, d.lr, frac=0.95 if d.enc_hidden else 0.99)
+    assert_params_close(P.cpu().numpy(), of, n_it, d.lr, frac=0.95 if d.enc_hidden else 0.99)
 
 
-@pytest.mark.parametrize("name", ["sphere_21_16_h200", "sigmoid_28_24", "wide_batch", "tc_route"])
+@pytest.mark.parametrize("name", ["sphere_21_16_h200", "sigmoid_28_24", "wide_batch", "tc_route", "cfg5_small"])
 def test_train_steps_well_conditioned_all_params(ops, lib, name):
     """Same as above with adam_eps = 1.0 (>> the absolute float32 gradient noise, which is
     ~1e-5 x max|g| and max|g| is O(10..100) here because 1/var_d = e^3): the m/sqrt(v)
@@ -235,12 +239,13 @@ def test_train_steps_well_conditioned_all_params(ops, lib, name):
     ws = ops.Workspace()
     of, om, ov, ostep = flat.astype(np.float64), np.zeros(d.n_params), np.zeros(d.n_params), 0
     L = d.latent_dim
-    for it in range(20):
+    n_it = 10 if d.n_params > 1_000_000 else 20
+    for it in range(n_it):
         _, x, z = make_inputs(d, seed=200 + it)
         ops.train_step(cd, P, M, V, step, dev(x), dev(z), loss, ws)
         of, om, ov, ostep, ol = vs.train_step(d, of, om, ov, ostep, x, z[:, :L], z[:, L:], dtype=np.float64)
         assert abs(float(loss) - ol) <= REL_STEP * abs(ol), f"step {it}"
-    assert_params_close(P.cpu().numpy(), of, 20, d.lr, frac=1.0)
+    assert_params_close(P.cpu().numpy(), of, n_it, d.lr, frac=1.0)
 
 
 @pytest.mark.parametrize("name", ["sigmoid_7_6", "sphere_21_16_h200"])
@@ -929,6 +934,34 @@ def test_fused_small_long_run(ops, lib, case, n):
     co.train_loop([cj], n, 1)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(st["mk"].cpu().numpy(), cj.model_key)      # 10k splits later: still bit-exact
+    np.testing.assert_array_equal(st["dk"].cpu().numpy(), cj.dataset_key)
+    _long_run_checks(d, st["loss"].cpu().numpy().astype(np.float64), cj.loss[:n].astype(np.float64),
+                     st["P"].cpu().numpy().astype(np.float64), cj.params.astype(np.float64), n)
+
+
+# The three sweeps' single-Dense lines at their REAL lengths (seed_linpadding_expts.sh:1 --num_batches 100000,
+# sigmoid_vae_padding_expts.sh:1 / :10 --num_batches 150000): what the paper reads off is the END of these runs
+FULL_LENGTH_CASES = [
+    (("linear_gaussian", 3, 9, 20, 1e-3, -1.0, 2), 100000),
+    (("sigmoid", 3, 3, 6, 1e-4, -3.0, 69), 150000),
+    (("sigmoid", 5, 5, 10, 1e-4, -3.0, 24), 150000),
+]
+
+
+@pytest.mark.parametrize("case,n", FULL_LENGTH_CASES, ids=lambda v: f"{v[0]}_dd{v[1]}_pd{v[2]}_L{v[3]}" if isinstance(v, tuple) else str(v))
+def test_fused_small_full_length_run(ops, lib, case, n):
+    """A whole sweep run in one persistent launch vs the float32 C oracle: both key chains bit-exact after 100 k /
+    150 k splits, the final learned variances (epsilon_p, epsilon * eps0: vae.py:137-138), every parameter and the
+    last 500 losses within 1e-3 (north_star's long-run bar, applied at 10x - 15x its 10 k steps)."""
+    d, ds, tr, st, job = fused_setup(ops, lib, case, n)
+    name, dd, pd = case[0], case[1], case[2]
+    flat = st["P"].cpu().numpy().copy()
+    co, cj = _c_oracle_job(d, ds, name, dd, pd, flat, tr.key, ds.key, n)
+    ops.train_fused([job], n, ops.fused_scratch(1))
+    co.train_loop([cj], n, 1)
+    torch.cuda.synchronize()
+    assert int(st["step"]) == n
+    np.testing.assert_array_equal(st["mk"].cpu().numpy(), cj.model_key)
     np.testing.assert_array_equal(st["dk"].cpu().numpy(), cj.dataset_key)
     _long_run_checks(d, st["loss"].cpu().numpy().astype(np.float64), cj.loss[:n].astype(np.float64),
                      st["P"].cpu().numpy().astype(np.float64), cj.params.astype(np.float64), n)

@@ -74,7 +74,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if proc.returncode != 0:
             sys.stderr.write(proc.stdout + proc.stderr)
             raise RuntimeError("nvcc failed linking libvae_b200.so")
+    build_xla_ffi_shim()
     return LIB
+
+
+def build_xla_ffi_shim(include_dir: str = "") -> str:
+    """g++ of csrc/xla_ffi_shim.cc -> libvae_b200_xla_ffi.so (the jax.ffi handlers over the C ABI).  The handlers
+    compile only where jaxlib's xla/ffi/api/ffi.h is found (include_dir, or `jax.ffi.include_dir()` when jax is
+    importable); otherwise the library exports just vae_xla_ffi_available() == 0."""
+    src = os.path.join(CSRC, "xla_ffi_shim.cc")
+    out = os.path.join(HERE, "libvae_b200_xla_ffi.so")
+    if not include_dir:
+        try:
+            import jax.ffi as jffi             # absent in this image: the shim then builds without handlers
+            include_dir = jffi.include_dir()
+        except Exception:
+            include_dir = ""
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(HEADER)) and not include_dir:
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", src, "-o", out]
+    if include_dir:
+        cmd += ["-I", include_dir, "-L", HERE, "-l:libvae_b200.so", "-Wl,-rpath,$ORIGIN"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed on xla_ffi_shim.cc")
+    return out
 
 
 if __name__ == "__main__":
