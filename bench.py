@@ -500,7 +500,8 @@ def measure_dp(ctx, workload, K, W):
                    learning_rate=w["lr"], epsilon=w["eps0"], tunable_decoder_var=True, dataset_seed=w["seed"])
     peak = tf32_peak(ctx)
     st = init.initial_state(spec)
-    model = dp.DataParallelVAE(spec, st.params, st.model_key, st.dataset_key, st.A)
+    model = dp.DataParallelVAE(spec, st.params, st.model_key, st.dataset_key, st.A,
+                               overlap=os.environ.get("VAE_DP_OVERLAP", "1") != "0")        # 0: A/B against one allreduce
     for _ in range(W):
         model.train_step()
     ctx.barrier()
@@ -548,7 +549,10 @@ def measure_dp(ctx, workload, K, W):
                       "l2_flush": "inputs larger than L2 (activations >= 1 GB per layer)",
                       "parallelism": f"dp{world}: row-pair sharded batch, " +
                                      (f"NCCL sum-allreduce of {(model.n + 1) * 4 / 1e6:.1f} MB per step, " if world > 1
-                                      else "no collective at one GPU, ") + "replicated Adam"},
+                                      else "no collective at one GPU, ") + "replicated Adam",
+                      "exchange": (f"{len(model.segments)} gradient segments (one per layer), each allreduced + Adam-updated on a "
+                                   "side stream as soon as the backward pass has produced it" if model.overlap
+                                   else "one allreduce of the whole gradient after the backward pass")},
            "e2e": {"value": 1.0 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 20,
                    "note": "inputs of a step are the two carried PRNG keys (batch and eps are generated on the device, "
                            "as in the reference); loss and keys are read back every step"},
