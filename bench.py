@@ -411,14 +411,15 @@ def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states
         raise SystemExit(f"bench.py: non-finite loss in the timed region ({workload})")
     total = n_models * ctx.world
     tensor_peak = None
-    if runs.plan.cls == 2 and runs.plan.cluster == 0:          # hidden-layer pack on the tensor-core kernel
+    if runs.plan.cls == 2 and runs.plan.tc:          # hidden-layer pack on the tensor-core kernel
         if "v" not in _TF32_PEAK:
             _TF32_PEAK["v"] = tf32_peak(ctx)
         tensor_peak = _TF32_PEAK["v"]
     out = {"value": total * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
            "models_per_gpu": n_models, "samples_per_sec": total * K / (ms * 1e-3) * specs[0].batch_size,
            "timing": {"repeats": R, "window_ms": window, "launch_ms_median": ms},
-           "launch_plan": {"class": runs.plan.cls, "models_per_cta": runs.plan.gm, "cluster": runs.plan.cluster},
+           "launch_plan": {"class": runs.plan.cls, "models_per_cta": runs.plan.gm, "cluster": runs.plan.cluster,
+                           "tensor_core_kernel": bool(runs.plan.tc)},
            "gpu_launches": int(launches),
            "kernel": ("fused_mlp_tc_kernel (tcgen05 3xTF32, one CTA per model)" if tensor_peak is not None else
                       "fused_mlp_kernel (FP32 FFMA, one cluster per model)" if runs.plan.cls == 2 else "fused_small_kernel"),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VAE_B200_ABI_VERSION 3
+#define VAE_B200_ABI_VERSION 4
 #define VAE_MAX_HIDDEN 8
 
 enum {
@@ -236,12 +236,13 @@ typedef struct VaePackPlan {
   int32_t shape_id;       /* class 1: kernel instance                               */
   int32_t homogeneous;    /* class 1: every job has the same shape and batch        */
   int32_t gm;             /* class 1: models per CTA                                */
-  int32_t cluster;        /* CTAs per thread-block cluster (class 2: 0 = tensor-core kernel, one CTA per model) */
+  int32_t cluster;        /* CTAs per thread-block cluster (class 2: CTAs per model)  */
   int32_t nbuf;           /* class 1: eps buffers (2 = drawn one step ahead)        */
   uint64_t smem_bytes;    /* dynamic shared memory per CTA                          */
   void* d_jobs;           /* device job table (= d_scratch)                         */
   int32_t device;         /* CUDA device the plan was prepared on                   */
-  int32_t reserved_[5];
+  int32_t tc;             /* class 2: 1 = tensor-core kernel (fused_mlp_tc.cu), 0 = FFMA cluster kernel */
+  int32_t reserved_[4];
 } VaePackPlan;
 int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, size_t scratch_bytes,
                      VaePackPlan* plan, void* stream);

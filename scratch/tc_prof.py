@@ -14,6 +14,6 @@ lib.vae_tc_profile(out, 1)
 runs.train_steps(K); torch.cuda.synchronize()
 lib.vae_tc_profile(out, 0)
 names = ["gemm chunk loop", "gemm + final acc wait", "adam normal", "adam transposed", "fwd epilogue", "dX epilogue", "rng + data", "whole step",
-         "  feeder: prologue loads", "  feeder: load (empty wait + tma)", "  feeder: ready wait", "  feeder: mma issue + commit",
+         "  producer: empty wait", "  producer: tma issue", "  mma thread: ready wait", "  mma thread: issue + commit",
          "  converter: full wait", "  converter: convert + arrive"]
 for n, v in zip(names, list(out)[:14]): print(f"{n:24s} {v / K:12.0f} cycles/step")

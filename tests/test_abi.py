@@ -49,7 +49,7 @@ def test_struct_layout_matches_header(lib):
 
 def test_host_side_helpers(lib):
     L = lib.load()
-    assert L.vae_abi_version() == 3
+    assert L.vae_abi_version() == 4
     d = lib.make_desc(100, 7, 6, sig_decoder=True)
     assert L.vae_param_count(C.byref(d)) == 153
     h = (200, 200, 200)

@@ -721,11 +721,12 @@ def test_fused_tc_vs_oracle_loop(ops, lib, case, monkeypatch):
     bit-exact, per-step loss rel 1e-5 (the TF32 hi/lo split with separate correction accumulators is as accurate as
     the FP32 FFMA kernel: 3e-7 .. 2e-6 measured), parameters within 1e-3 lr per step."""
     monkeypatch.setenv("VAE_MLP_TC", "1")
+    monkeypatch.setenv("VAE_MLP_TC_CLUSTER", "1")
     n = 12
     d, ds, tr, st, job = mlp_setup(ops, lib, case, n)
     sc = ops.fused_scratch(1)
     plan = ops.pack_prepare([job], sc)
-    assert plan.cls == 2 and plan.cluster == 0          # cluster 0 = the tensor-core kernel
+    assert plan.cls == 2 and plan.tc == 1 and plan.cluster == 1      # the tensor-core kernel, one CTA per model
     ops.pack_train(plan, n)
     torch.cuda.synchronize()
     tr.train(10 ** 9, start=0, stop=n, events=False)
@@ -745,6 +746,7 @@ def test_fused_tc_packed_chunked_and_deterministic(ops, lib, monkeypatch):
     the flat C-ABI vectors between launches) change nothing, bit for bit; and the FFMA cluster kernel agrees with the
     tensor-core kernel to float32 round-off."""
     monkeypatch.setenv("VAE_MLP_TC", "1")
+    monkeypatch.setenv("VAE_MLP_TC_CLUSTER", "1")
     n = 9
     cases = (MLP_CASES[0], MLP_CASES[2], MLP_CASES[5], MLP_CASES[6])
     singles, packed = [], []
@@ -770,8 +772,48 @@ def test_fused_tc_packed_chunked_and_deterministic(ops, lib, monkeypatch):
         assert np.max(np.abs(la - lb) / np.abs(lb)) <= REL_STEP
 
 
+@pytest.mark.parametrize("cs", [2, 4, 8])
+def test_fused_tc_cluster_sizes_are_bit_identical(ops, lib, monkeypatch, cs):
+    """The latency configuration of the tensor-core kernel -- one model on a thread-block cluster of 2 / 4 / 8 CTAs,
+    every GEMM cut along N in 8-column groups, narrow layers on CTA 0 -- produces bit for bit what one CTA per model
+    produces: every output element is the same MMA sequence.  (Any missing cluster barrier / proxy fence between a
+    producer's global stores and a peer's TMA reads shows up here as a mismatch.)  Covers every hidden-layer shape of
+    the tests, single launches and a chunked multi-model pack; auto-selection picks a cluster for a small pack."""
+    monkeypatch.setenv("VAE_MLP_TC", "1")
+    n = 10
+    ref, test = [], []
+    for case in MLP_CASES:
+        monkeypatch.setenv("VAE_MLP_TC_CLUSTER", "1")
+        _, _, _, st, job = mlp_setup(ops, lib, case, n)
+        ops.train_fused([job], n, ops.fused_scratch(1))
+        ref.append(st)
+        monkeypatch.setenv("VAE_MLP_TC_CLUSTER", str(cs))
+        _, _, _, st2, job2 = mlp_setup(ops, lib, case, n)
+        sc = ops.fused_scratch(1)
+        plan = ops.pack_prepare([job2], sc)
+        assert plan.cls == 2 and plan.tc == 1 and plan.cluster == cs
+        ops.pack_train(plan, n)
+        torch.cuda.synchronize()
+        for k in ("P", "M", "V", "mk", "dk", "step", "loss"):
+            assert torch.equal(st[k], st2[k]), (case, k)
+        test.append(mlp_setup(ops, lib, case, n)[3:])
+    # all shapes in ONE launch (one cluster each), steps split over three launches
+    sc = ops.fused_scratch(len(test))
+    for chunk in (3, 1, 6):
+        ops.train_fused([j for _, j in test], chunk, sc)
+        torch.cuda.synchronize()
+    for a, (b, _) in zip(ref, test):
+        for k in ("P", "M", "V", "mk", "dk", "step"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a["loss"][4:10], b["loss"][:6])
+    monkeypatch.delenv("VAE_MLP_TC_CLUSTER")
+    _, _, _, _, job = mlp_setup(ops, lib, MLP_CASES[0], n)
+    assert ops.pack_prepare([job], ops.fused_scratch(1)).cluster == 8        # a lone chain gets the largest cluster
+
+
 def test_fused_tc_nonzero_moments_on_padding_rows(ops, lib, monkeypatch):
     monkeypatch.setenv("VAE_MLP_TC", "1")
+    monkeypatch.setenv("VAE_MLP_TC_CLUSTER", "4")
     n = 8
     case = MLP_CASES[1]
     d, ds, tr, st, job = mlp_setup(ops, lib, case, n)

@@ -50,7 +50,7 @@ class VaePackPlan(C.Structure):
     _fields_ = [
         ("abi", C.c_int32), ("cls", C.c_int32), ("n_jobs", C.c_int32), ("shape_id", C.c_int32),
         ("homogeneous", C.c_int32), ("gm", C.c_int32), ("cluster", C.c_int32), ("nbuf", C.c_int32),
-        ("smem_bytes", C.c_uint64), ("d_jobs", C.c_void_p), ("device", C.c_int32), ("reserved_", C.c_int32 * 5),
+        ("smem_bytes", C.c_uint64), ("d_jobs", C.c_void_p), ("device", C.c_int32), ("tc", C.c_int32), ("reserved_", C.c_int32 * 4),
     ]
 
 

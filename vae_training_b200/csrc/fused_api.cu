@@ -5,6 +5,10 @@
 
 #include "common.cuh"
 
+#ifndef VAE_MLP_TC_MIN_JOBS
+#define VAE_MLP_TC_MIN_JOBS 16     // smaller packs stay on the FFMA cluster kernel (8 - 16 CTAs per model: 148 - 170 us/step vs 185; profiles/r02_mlp_kernel_crossover.txt)
+#endif
+
 namespace vae {
 // fused_small.cu
 int small_supported(const VaeTrainJob* job);
@@ -23,15 +27,15 @@ int mlp_resident_jobs(size_t smem, size_t smem4, int* out);
 // fused_mlp_tc.cu (tensor-core kernel for the same class-2 jobs; one CTA per model)
 int mlp_tc_supported(const VaeTrainJob* j, size_t* ws_bytes);
 size_t mlp_tc_job_bytes();
-int mlp_tc_fill_job(const VaeTrainJob& j, void* out);
-int mlp_tc_prepare();
+int mlp_tc_fill_job(const VaeTrainJob& j, void* out, int csize);
+int mlp_tc_prepare(int n_jobs, int* cluster);
 int mlp_tc_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s);
 
-// Which kernel runs a class-2 pack.  The tensor-core kernel (one CTA per model, ~430 us per step however many models
-// are resident) wins on THROUGHPUT once a pack is large enough to fill the GPU with single-CTA models -- measured on
-// B200: 148 models 282 k steps/s vs 155 k for the FFMA kernel, break-even near 64 models -- while the FFMA cluster
-// kernel (8 - 16 CTAs per model, 147 - 169 us per step) wins on LATENCY for small packs.  VAE_MLP_TC=1 / 0 forces.
-constexpr int kMlpTcMinJobs = 64;
+// Which kernel runs a class-2 pack.  The tensor-core kernel runs one model per CTA (throughput: packs that fill the
+// GPU) or per cluster of 2 / 4 / 8 CTAs (latency: small packs, e.g. the two sphere chains per GPU of the 8-GPU sweep);
+// the FFMA cluster kernel of fused_mlp.cu stays as the fallback for shapes the tensor-core kernel does not take
+// (batch > 128, sigmoid decoders, layers wider than 200).  VAE_MLP_TC=1 / 0 forces one or the other (A/B runs).
+constexpr int kMlpTcMinJobs = VAE_MLP_TC_MIN_JOBS;
 static bool use_mlp_tc(const VaeTrainJob* j, size_t* ws, int n_jobs) {
   const char* e = getenv("VAE_MLP_TC");
   if (e && e[0] == '0') return false;
@@ -119,6 +123,8 @@ int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, s
     bool tc = true;
     for (int i = 0; i < n_jobs && tc; ++i) tc = vae::use_mlp_tc(&jobs[i], nullptr, n_jobs);
     if (tc) {
+      int tcs = 1;
+      if ((rc = vae::mlp_tc_prepare(n_jobs, &tcs))) return rc;
       const size_t tjb = vae::mlp_tc_job_bytes();
       char* th = (char*)malloc((size_t)n_jobs * tjb);
       VAE_REQUIRE(th, "vae_pack_prepare: out of host memory");
@@ -131,14 +137,13 @@ int vae_pack_prepare(const VaeTrainJob* jobs, int32_t n_jobs, void* d_scratch, s
                          "vae_train_fused_workspace_bytes() bytes)", i);
           return VAE_ERR_INVALID;
         }
-        rc = vae::mlp_tc_fill_job(j, th + (size_t)i * tjb);
+        rc = vae::mlp_tc_fill_job(j, th + (size_t)i * tjb, tcs);
         if (rc) { free(th); return rc; }
       }
       cudaError_t e = cudaMemcpyAsync(d_scratch, th, (size_t)n_jobs * tjb, cudaMemcpyHostToDevice, s);
       free(th);
       VAE_CUDA_OK(e);
-      if ((rc = vae::mlp_tc_prepare())) return rc;
-      plan->cls = 2; plan->n_jobs = n_jobs; plan->d_jobs = d_scratch; plan->cluster = 0; plan->smem_bytes = 0;
+      plan->cls = 2; plan->n_jobs = n_jobs; plan->d_jobs = d_scratch; plan->cluster = tcs; plan->tc = 1; plan->smem_bytes = 0;
       plan->abi = VAE_B200_ABI_VERSION;
       plan->device = dev;
       return 0;
@@ -181,7 +186,7 @@ int vae_pack_train(const VaePackPlan* plan, int64_t n_steps, void* stream) {
               "vae_pack_train: plan was not produced by vae_pack_prepare of this library version");
   if (n_steps == 0) return 0;
   if (plan->cls == 1) return vae::small_launch(plan, n_steps, (cudaStream_t)stream);
-  if (plan->cls == 2 && plan->cluster == 0) return vae::mlp_tc_launch(plan, n_steps, (cudaStream_t)stream);
+  if (plan->cls == 2 && plan->tc) return vae::mlp_tc_launch(plan, n_steps, (cudaStream_t)stream);
   if (plan->cls == 2) return vae::mlp_launch(plan, n_steps, (cudaStream_t)stream);
   vae::set_error("vae_pack_train: bad plan class %d", plan->cls);
   return VAE_ERR_INVALID;

@@ -38,6 +38,15 @@
 // the accumulator (128 lanes x N columns per M tile) is drained with tcgen05.ld by all 16 warps (lane quarter =
 // warp % 4, column groups dealt round-robin to the four warps of a quarter) into the fused epilogue: bias + relu,
 // relu mask, reparameterisation, loss partials, or Adam.
+//
+// Latency configuration: a thread-block CLUSTER of C = 2, 4 or 8 CTAs per model.  Every GEMM is cut along its N
+// dimension in units of 8 columns (tc_slice): forward Y[:, slice], dX[:, k-slice], dW[:, slice] + Adam on the slice;
+// a CTA loads only its rows of the B operand (TMA row coordinate) and the whole A operand, multiplies M128 x Nslice
+// and writes its slice of the result to the same global (L2-resident) arrays as the single-CTA kernel; one hardware
+// cluster barrier (release / acquire, after a generic->async proxy fence so the peers' TMA reads see the stores)
+// per GEMM on the dependent chain: 1 + 8 + 7 = 16 per step.  Layers of at most 64 columns (mu, x_hat, the latent
+// gradient) belong to CTA 0 alone, which therefore also owns the loss and the epsilon / epsilon_p updates.  Every
+// output element is produced by the same MMA sequence whatever C is: results are bit-identical for C = 1, 2, 4, 8.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,10 +64,26 @@ constexpr int kTMaxN = 208;                     // most B rows (accumulator colu
 constexpr int kTRingBytes = 176 * 1024;         // the operand ring; a GEMM cuts it into stages of its own size
 constexpr int kTSmemBytes = kTRingBytes + 1024;
 constexpr int kTMaxL = VAE_MAX_HIDDEN + 1;
+constexpr int kTMaxCluster = 8;                 // CTAs per model in the latency configuration (portable cluster size)
+constexpr int kTNarrowGroups = 8;               // layers of at most this many 8-column groups are not cut (CTA 0 owns them)
 // tensor maps of a model: per layer [W^T, W (group-major), input batch-major, input feature-major, dY feature-major],
-// then the two batch-major gradient buffers
+// then the three batch-major gradient buffers
 enum { TM_WT = 0, TM_W8 = 1, TM_INBM = 2, TM_INT = 3, TM_GT = 4, TM_PER_LAYER = 5 };
-constexpr int kTMaps = 2 * kTMaxL * TM_PER_LAYER + 2;
+constexpr int kTGradBufs = 3;                   // dY buffers in rotation (see the backward pass)
+constexpr int kTMaps = 2 * kTMaxL * TM_PER_LAYER + kTGradBufs;
+
+// Columns [8 g0, 8 g1) of a layer with `groups` 8-column groups that CTA `rank` of a `csize`-CTA cluster owns.
+__host__ __device__ inline void tc_slice(int groups, int csize, int rank, int* g0, int* g1) {
+  if (csize <= 1 || groups <= kTNarrowGroups) { *g0 = 0; *g1 = rank == 0 ? groups : 0; return; }
+  const int base = groups / csize, rem = groups % csize;
+  *g0 = rank * base + (rank < rem ? rank : rem);
+  *g1 = *g0 + base + (rank < rem ? 1 : 0);
+}
+// Rows of the B-operand TMA box of such a layer (the widest slice; every CTA multiplies this many columns)
+__host__ __device__ inline int tc_slice_box(int groups, int csize) {
+  if (csize <= 1 || groups <= kTNarrowGroups) return groups * 8;
+  return ((groups + csize - 1) / csize) * 8;
+}
 
 __host__ __device__ constexpr int t_up8(int n) { return (n + 7) & ~7; }
 __host__ __device__ constexpr int t_up4(int n) { return (n + 3) & ~3; }
@@ -72,7 +97,8 @@ struct TcLayer {
   int32_t in_bm, in_T;             // layer input: batch-major [BP][Kp], feature-major [Kp + 8][BP] (row Kuse = ones)
   int32_t out_bm, out_T;           // layer output (hidden layers): batch-major [BP][Np], feature-major [Np + 8][BP]
   int32_t in_mask, out_mask;       // relu masks (output > 0) of the input / output activation: [BP][32] bytes, one per 8 columns
-  int32_t gcur;                    // which of the two gradient buffers holds this layer's dY in the backward pass
+  int32_t gcur;                    // which of the three gradient buffers holds this layer's dY in the backward pass
+  int32_t nbox, kbox;              // B-operand box rows of the N-sliced (forward, dW) and K-sliced (dX) GEMMs
 };
 
 struct TcJobDev {
@@ -82,8 +108,8 @@ struct TcJobDev {
   int32_t Lp, Dp, LD;
   int32_t off_lv, off_eps;         // flat offsets of epsilon_p, epsilon
   int32_t pm_stride;               // floats between the aligned P, M and V parameter regions
-  int32_t ws_z, ws_gn, ws_mu, ws_gbm[2], ws_gT[2];
-  int32_t n_flat;
+  int32_t ws_z, ws_gn, ws_mu, ws_gbm[kTGradBufs], ws_gT[kTGradBufs];
+  int32_t n_flat, csize;
   TcLayer enc[kTMaxL], dec[kTMaxL];
   float eps0, lr, b1, b2, omb1, omb2, adam_eps;
   alignas(64) CUtensorMap maps[kTMaps];   // read by TMA straight from the job table in global memory
@@ -109,6 +135,15 @@ __device__ __forceinline__ void t_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void t_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(bar)) : "memory");
 }
+// One lane of the (converged) warp: 1 in the elected lane, 0 elsewhere.
+__device__ __forceinline__ uint32_t t_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+// Marks a value the whole warp holds identically as warp-uniform for the compiler (it then lives in a uniform register
+// and feeds UTCHMMA / UTMALDG directly instead of through a per-instruction ELECT + R2UR waterfall).
+__device__ __forceinline__ uint32_t t_uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void t_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -133,14 +168,16 @@ __device__ __forceinline__ void t_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 // one chunk (16 K floats) of the operand's box rows: row-major operands are a 2-D map {K floats, rows} (box 16 x rows),
 // group-major ones a 3-D map {8 floats, rows, K groups} (box 8 x rows x 2)
-__device__ __forceinline__ void t_tma_chunk(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int chunk, int grouped) {
+__device__ __forceinline__ void t_tma_chunk(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int chunk, int grouped, int row0) {
   if (grouped)
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %3, %4}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(0), "r"(2 * chunk) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(0), "r"(row0), "r"(2 * chunk) : "memory");
   else
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(16 * chunk), "r"(0) : "memory");
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(t_smem(bar)), "r"(16 * chunk), "r"(row0) : "memory");
 }
+__device__ __forceinline__ uint32_t t_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t t_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 // 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void t_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -198,15 +235,20 @@ __device__ __forceinline__ float t_adam(float p, float& m, float& v, float g, co
 
 #ifdef VAE_TC_PROFILE
 __device__ long long g_tc_prof[16];
-#define TC_LAPS() long long _tl = clock64()
-#define TC_LAP(i) do { if (blockIdx.x == 0) { const long long _n = clock64(); g_tc_prof[i] += _n - _tl; _tl = _n; } } while (0)
+// per-role lap timers: accumulated in registers inside a GEMM, added to the global counters once per GEMM
+#define TC_LAPS() long long _tl = clock64(), _la = 0, _lb = 0
+#define TC_LAP_A() do { const long long _n = clock64(); _la += _n - _tl; _tl = _n; } while (0)
+#define TC_LAP_B() do { const long long _n = clock64(); _lb += _n - _tl; _tl = _n; } while (0)
+#define TC_LAP_FLUSH(i, j) do { if (blockIdx.x == 0) { g_tc_prof[i] += _la; g_tc_prof[j] += _lb; } } while (0)
 #define TC_T0() const long long _t0 = clock64()
 #define TC_ACC(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_prof[i] += clock64() - _t0; } while (0)
 #else
 #define TC_T0() do {} while (0)
 #define TC_ACC(i) do {} while (0)
 #define TC_LAPS() do {} while (0)
-#define TC_LAP(i) do {} while (0)
+#define TC_LAP_A() do {} while (0)
+#define TC_LAP_B() do {} while (0)
+#define TC_LAP_FLUSH(i, j) do {} while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------ GEMM main loop
@@ -226,18 +268,19 @@ struct TcRing {
 };
 
 // A GEMM operand: its tensor map (box = box_rows x 16 K floats), whether the global array is group-major, box rows.
-struct TcOperand { const CUtensorMap* tm; int grouped; int box_rows; };
+struct TcOperand { const CUtensorMap* tm; int grouped; int box_rows; int row0 = 0; };
 
 // D[m][n] = sum_k A[m][k] B[n][k], k < kpad (multiple of 8).  A: m_tiles M tiles of 128 rows out of A.box_rows; B:
 // B.box_rows rows, n_mma (multiple of 8) of them multiplied.  bias (may be null): n_bias floats copied to R.bias_s
 // while the main loop runs.  The ring is cut into stages of this GEMM's own size, (A.box_rows + B.box_rows) x 16
 // floats x {hi, lo}: [A hi][B hi][A lo][B lo]; up to stages - 1 chunks are in flight beyond the one being multiplied.
-// Roles: thread 0 feeds the ring (TMA) and issues the MMAs; warps 1..15 split the landed chunks into hi / lo and hand
-// them over through the `ready` barriers -- no block-wide barrier inside the loop, so the split of chunk c + 1 runs
-// under the MMAs of chunk c.  On return the accumulator is complete and visible to tcgen05.ld in every thread.
+// Roles: lane 0 of warp 0 feeds the ring (TMA), lane 0 of warp 1 issues the MMAs (a single thread doing both spends
+// ~1.4 k cycles of dependent scalar code per chunk, whatever N is -- measured), warps 2..15 split the landed chunks
+// into hi / lo and hand them over through the `ready` barriers -- no block-wide barrier inside the loop, so the load of
+// chunk c + 2, the split of chunk c + 1 and the MMAs of chunk c overlap.  On return the accumulator is complete and visible to tcgen05.ld in every thread.
 __device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int m_tiles, const TcOperand Bm, int n_mma, int kpad,
                                         const float* __restrict__ bias = nullptr, int n_bias = 0) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = (kpad + kTKC - 1) / kTKC;
   const int a_bytes = A.box_rows * kTKC * 4, b_bytes = Bm.box_rows * kTKC * 4, hi_bytes = a_bytes + b_bytes;
   const int stage_bytes = 2 * hi_bytes;
@@ -246,74 +289,107 @@ __device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int m_tile
 
   TC_T0();
   if (tid == 0) {
-    // ===================== feeding thread: TMA producer + MMA issuer
-    const uint32_t idesc = t_idesc(n_mma);
-    auto load = [&](int c) {
-      const int stage = c % nstages;
+    // ===================== producer thread: one TMA box per operand and chunk, as far ahead as the ring allows
+    int stage = 0;
+    TC_LAPS();
+    for (int c = 0; c < nchunk; ++c) {
       if (R.pend & (1u << stage)) {                // the MMAs that read this slot have retired
         t_mbar_wait(&R.empty[stage], (R.par >> stage) & 1u);
-        R.par ^= 1u << stage; R.pend &= ~(1u << stage);
+        R.par ^= 1u << stage;
       }
-      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes);
+      TC_LAP_A();
+      R.pend |= 1u << stage;                       // a commit on empty[stage] will follow this chunk's MMAs
+      const uint32_t sA = t_smem(R.base) + (uint32_t)(stage * stage_bytes);
       t_expect_tx(&R.full[stage], (uint32_t)hi_bytes);
-      t_tma_chunk(sA, A.tm, &R.full[stage], c, A.grouped);
-      t_tma_chunk(sA + a_bytes, Bm.tm, &R.full[stage], c, Bm.grouped);
-    };
-    TC_LAPS();
-    for (int c = 0; c < nstages - 1 && c < nchunk; ++c) load(c);
-    TC_LAP(8);
-    for (int c = 0; c < nchunk; ++c) {
-      const int stage = c % nstages;
-      if (c + nstages - 1 < nchunk) load(c + nstages - 1);            // the slot of chunk c - 1 (its MMAs were queued last iteration)
-      TC_LAP(9);
-      t_mbar_wait(&R.ready[stage], (R.rpar >> stage) & 1u);            // chunk c is split into hi / lo
-      R.rpar ^= 1u << stage;
-      TC_LAP(10);
-      t_fence_after();
-      const uint32_t sA = t_smem(R.base + (size_t)stage * stage_bytes), sB = sA + a_bytes;
-      const int ksteps = min(kTKC, kpad - c * kTKC) >> 3;
-      for (int s = 0; s < ksteps; ++s) {
-        // K = 8 step s: +32 bytes inside the 64-byte rows (row-major) / the next [row][32 B] group block (group-major)
-        const uint32_t ka = (uint32_t)(A.grouped ? s * A.box_rows * 32 : s * 32);
-        const uint32_t kb = (uint32_t)(Bm.grouped ? s * Bm.box_rows * 32 : s * 32);
-        const uint64_t dBh = t_desc(sB + kb, Bm.grouped), dBl = t_desc(sB + hi_bytes + kb, Bm.grouped);
-        for (int t = 0; t < m_tiles; ++t) {
-          const uint32_t ta = (uint32_t)(t * 128 * (A.grouped ? 32 : 64));                  // M tile t: 128 rows further
-          const uint64_t dAh = t_desc(sA + ka + ta, A.grouped), dAl = t_desc(sA + hi_bytes + ka + ta, A.grouped);
-          const uint32_t d = R.tmem + (uint32_t)(t * 256);
-          // The tensor core accumulates FP32 with round-toward-zero.  Single-tile GEMMs (forward, dX: K up to 200)
-          // keep the two correction products in their own accumulator (columns 256..) so that the small terms are
-          // never truncated against the large main sum and the main chain is a third as long; the epilogue adds
-          // the two.  Two-tile GEMMs (dW, K = batch) have no columns to spare and a chain of only 39 MMAs.
-          const uint32_t dc = m_tiles == 1 ? d + 256u : d;
-          t_mma(d, dAh, dBh, idesc, (c | s) != 0);
-          t_mma(dc, dAh, dBl, idesc, m_tiles == 1 ? (uint32_t)((c | s) != 0) : 1u);
-          t_mma(dc, dAl, dBh, idesc, 1u);
-        }
-      }
-      t_commit(&R.empty[stage]);
-      R.pend |= 1u << stage;
-      if (c == nchunk - 1) t_commit(R.accfull);
-      TC_LAP(11);
+      t_tma_chunk(sA, A.tm, &R.full[stage], c, A.grouped, A.row0);
+      t_tma_chunk(sA + a_bytes, Bm.tm, &R.full[stage], c, Bm.grouped, Bm.row0);
+      stage = stage + 1 == nstages ? 0 : stage + 1;
+      TC_LAP_B();
     }
-  } else if (tid >= 32) {
+    TC_LAP_FLUSH(8, 9);
+  } else if (warp == 1) {
+    // ===================== MMA warp: waits for a chunk's hi / lo split, queues its MMAs (one elected lane), frees the
+    // slot by commit.  The whole warp runs the loop on warp-uniform values: descriptors are built in uniform registers.
+    const uint32_t idesc = t_uni(t_idesc(n_mma));
+    // descriptor = constant high part | (shared address >> 4); the ring lies below 256 KB, so the address field never carries
+    const uint64_t hA = t_desc(0, A.grouped), hB = t_desc(0, Bm.grouped);
+    const uint32_t hiA = t_uni((uint32_t)(hA >> 32)), loA = t_uni((uint32_t)hA), hiB = t_uni((uint32_t)(hB >> 32)), loB = t_uni((uint32_t)hB);
+    const uint32_t ka = t_uni((uint32_t)(A.grouped ? A.box_rows * 32 : 32) >> 4);       // one K = 8 step further, in descriptor units:
+    const uint32_t kb = t_uni((uint32_t)(Bm.grouped ? Bm.box_rows * 32 : 32) >> 4);     // +32 B in a 64-byte row / the next group block
+    const uint32_t ta = t_uni((uint32_t)(128 * (A.grouped ? 32 : 64)) >> 4);            // M tile 1: 128 rows further
+    const uint32_t lo_ofs = t_uni((uint32_t)hi_bytes >> 4), b_ofs = t_uni((uint32_t)a_bytes >> 4), st_ofs = t_uni((uint32_t)stage_bytes >> 4);
+    const uint32_t ring = t_uni(t_smem(R.base) >> 4), tmem = t_uni(R.tmem);
+    const uint32_t un_chunk = t_uni((uint32_t)nchunk), un_stages = t_uni((uint32_t)nstages), u_kpad = t_uni((uint32_t)kpad);
+    const uint32_t two_tiles = t_uni((uint32_t)(m_tiles != 1));
+    uint32_t rpar = t_uni(R.rpar);
+    auto desc = [](uint32_t hi, uint32_t lo) -> uint64_t { return ((uint64_t)hi << 32) | lo; };
+    uint32_t stage = 0;
+    TC_LAPS();
+    for (uint32_t c = 0; c < un_chunk; ++c) {
+      t_mbar_wait(&R.ready[stage], (rpar >> stage) & 1u);              // chunk c is split into hi / lo
+      rpar ^= 1u << stage;
+      TC_LAP_A();
+      t_fence_after();
+      const uint32_t sA = ring + stage * st_ofs, sB = sA + b_ofs;
+      const uint32_t ksteps = min((uint32_t)kTKC, u_kpad - c * kTKC) >> 3;
+      if (t_elect()) {
+#pragma unroll
+        for (uint32_t s = 0; s < kTKC / 8; ++s) {
+          if (s < ksteps) {
+            const uint64_t dBh = desc(hiB, loB | (sB + s * kb)), dBl = desc(hiB, loB | (sB + lo_ofs + s * kb));
+            const uint32_t acc = (uint32_t)((c | s) != 0);
+            if (!two_tiles) {
+              // The tensor core accumulates FP32 with round-toward-zero.  Single-tile GEMMs (forward, dX: K up to 200)
+              // keep the two correction products in their own accumulator (columns 256..) so that the small terms are
+              // never truncated against the large main sum and the main chain is a third as long; the epilogue adds
+              // the two.  Two-tile GEMMs (dW, K = batch) have no columns to spare and a chain of only 39 MMAs.
+              const uint64_t dAh = desc(hiA, loA | (sA + s * ka)), dAl = desc(hiA, loA | (sA + lo_ofs + s * ka));
+              t_mma(tmem, dAh, dBh, idesc, acc);
+              t_mma(tmem + 256u, dAh, dBl, idesc, acc);
+              t_mma(tmem + 256u, dAl, dBh, idesc, 1u);
+            } else {
+#pragma unroll
+              for (uint32_t t = 0; t < 2; ++t) {
+                const uint64_t dAh = desc(hiA, loA | (sA + s * ka + t * ta)), dAl = desc(hiA, loA | (sA + lo_ofs + s * ka + t * ta));
+                const uint32_t d = tmem + t * 256u;
+                t_mma(d, dAh, dBh, idesc, acc);
+                t_mma(d, dAh, dBl, idesc, 1u);
+                t_mma(d, dAl, dBh, idesc, 1u);
+              }
+            }
+          }
+        }
+        t_commit(&R.empty[stage]);
+        if (c == un_chunk - 1) t_commit(R.accfull);
+      }
+      __syncwarp();
+      TC_LAP_B();
+      stage = stage + 1 == un_stages ? 0 : stage + 1;
+    }
+    R.rpar = rpar;
+    if (lane == 0) TC_LAP_FLUSH(10, 11);
+  } else if (tid >= 64) {
     // ===================== converter warps: hi = TF32(x) rounded to nearest (in place), lo = x - hi
-    const int ct = tid - 32;
+    // A chunk costs a warp ~600 cycles whatever its size (barrier wake-up, proxy fence, arrive -- measured), so with an
+    // even number of ring slots the 14 warps work as two groups on alternate chunks (a slot then always belongs to the
+    // same group, which keeps every thread's parity bookkeeping of the slot's `full` barrier exact).
+    const int ngrp = (nstages & 1) ? 1 : 2;
+    const int grp = ngrp == 2 ? (warp & 1) : 0;
+    const int ct = ngrp == 2 ? ((warp - 2) >> 1) * 32 + lane : tid - 64;
+    const int nconv = (kTT - 64) / ngrp;
     if (bias != nullptr)
-      for (int i = ct; i < n_bias; i += kTT - 32) R.bias_s[i] = bias[i];
+      for (int i = tid - 64; i < n_bias; i += kTT - 64) R.bias_s[i] = bias[i];
     const int n4 = hi_bytes >> 4;
-    for (int c = 0; c < nchunk; ++c) {
-      const int stage = c % nstages;
-#ifdef VAE_TC_PROFILE
-      long long _tl = clock64();
-#endif
-      t_mbar_wait(&R.full[stage], (R.fpar >> stage) & 1u);             // the chunk's two boxes have landed
-      R.fpar ^= 1u << stage;
-      if (tid == 32) TC_LAP(12);
+    int stage = grp;
+    uint32_t use = 0;                                                  // completions of full[stage] earlier in this GEMM
+    TC_LAPS();
+    for (int c = grp; c < nchunk; c += ngrp) {
+      t_mbar_wait(&R.full[stage], ((R.fpar >> stage) ^ use) & 1u);     // the chunk's two boxes have landed
+      TC_LAP_A();
       float4* hi = reinterpret_cast<float4*>(R.base + (size_t)stage * stage_bytes);
       float4* lo = reinterpret_cast<float4*>(R.base + (size_t)stage * stage_bytes + hi_bytes);
 #pragma unroll 3
-      for (int p = ct; p < n4; p += kTT - 32) {
+      for (int p = ct; p < n4; p += nconv) {
         const float4 x = hi[p];
         // hi rounded to nearest, not the hardware's truncation of a raw operand: with truncation lo >= 0 always and the
         // dropped Al.Bl term biases every product the same way (measured: loss error 3.9e-6 instead of 2.0e-6)
@@ -323,11 +399,19 @@ __device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int m_tile
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy smem writes -> tensor-core reads
       __syncwarp();
-      if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_smem(&R.ready[stage])) : "memory");
-      if (tid == 32) TC_LAP(13);
+      if (lane == 0)                                                   // ready[] counts 14 arrivals per chunk
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem(&R.ready[stage])), "r"(ngrp) : "memory");
+      TC_LAP_B();
+      stage += ngrp;
+      if (stage >= nstages) { stage -= nstages; ++use; }
     }
+    if (tid == 64) TC_LAP_FLUSH(12, 13);
   }
+  // every thread's view of the `full` barriers' parities: slot s completed once per chunk c = s (mod nstages)
+  for (int st = 0; st < nstages && st < nchunk; ++st)
+    if (((nchunk - st + nstages - 1) / nstages) & 1) R.fpar ^= 1u << st;
   TC_ACC(0);
+  if (tid < 32) __syncwarp();                      // lanes 1..31 of the producer warp park here instead of polling beside lane 0
   t_mbar_wait(R.accfull, R.gemms & 1u);
   TC_ACC(1);
   R.gemms += 1;
@@ -340,6 +424,17 @@ __device__ __forceinline__ void tc_gemm(TcRing& R, const TcOperand A, int m_tile
 __device__ __forceinline__ void tc_epilogue_done() {
   t_fence_before();
   __syncthreads();
+}
+// The same across the model's cluster: this CTA's global stores are ordered before every peer's later reads -- generic
+// (epilogue loads) through the barrier's release / acquire, async-proxy (TMA) through the proxy fence before it.
+__device__ __forceinline__ void tc_cluster_sync(int csize) {
+  t_fence_before();
+  if (csize > 1) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
 }
 
 __device__ __forceinline__ float tc_block_sum(float v, float* red) {   // result valid in every thread
@@ -356,18 +451,17 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {   // result
 // Element (k, n) of a layer's group-major W / m / v copy (see the header): [n / 8][k][8]
 __device__ __forceinline__ size_t tc_w8(const TcLayer& Ly, int k, int n) { return ((size_t)(n >> 3) * Ly.K + k) * 8 + (n & 7); }
 
-// Adam epilogue of dW in the NORMAL orientation: accumulator row = k (M tile t, lane r -> k = 128 t + r), column = n.
-// Row Kuse is the bias (the ones row of X^T).  Updates W / m / v (group-major: one 256-bit access per lane and column
-// group, lanes contiguous) and W^T.  The parameter / moment loads of the next two column groups are in flight while a
-// group is updated (the state lives in L2 / HBM).
+// Adam epilogue of dW: accumulator row = k (M tile t, lane r -> k = 128 t + r), column = n - 8 g0 for the column groups
+// [g0, g1) this CTA owns.  Row Kuse is the bias (the ones row of X^T).  Updates W / m / v (group-major: one 256-bit access
+// per lane and column group, lanes contiguous) and W^T.  The parameter / moment loads of the next two column groups are
+// in flight while a group is updated (the state lives in L2 / HBM).
 struct TcPmv { float p[8], m[8], v[8]; };
 __device__ __forceinline__ void tc_pmv_load(const float* P, int pm, TcPmv& x) {
   t_ldg8(P, x.p); t_ldg8(P + pm, x.m); t_ldg8(P + 2 * pm, x.v);
 }
-__device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
-                                               const TcHyper& hp) {
+__device__ __forceinline__ void tc_adam(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
+                                        int g0, int g1, const TcHyper& hp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, cg = warp >> 2;
-  const int ngroups = Ly.Np >> 3;
   for (int t = 0; t < m_tiles; ++t) {
     if (t * 128 + q * 32 > Ly.Kuse) continue;                        // no row of this warp's lane quarter is a parameter
     const int k = t * 128 + q * 32 + lane;
@@ -376,12 +470,12 @@ __device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restric
     const float* base = is_b ? ws + Ly.Bv : ws + Ly.W + (size_t)(live ? k : 0) * 8;
     const size_t gstride = is_b ? 8 : (size_t)Ly.K * 8;
     TcPmv cur, nxt;
-    if (live && cg < ngroups) tc_pmv_load(base + cg * gstride, pm, cur);
-    for (int g = cg; g < ngroups; g += kTCG) {
-      if (live && g + kTCG < ngroups) tc_pmv_load(base + (g + kTCG) * gstride, pm, nxt);      // in flight during the update of g
+    if (live && g0 + cg < g1) tc_pmv_load(base + (g0 + cg) * gstride, pm, cur);
+    for (int g = g0 + cg; g < g1; g += kTCG) {
+      if (live && g + kTCG < g1) tc_pmv_load(base + (g + kTCG) * gstride, pm, nxt);      // in flight during the update of g
       float acc[8];
-      if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
-      else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
+      if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g0) * 8), acc);
+      else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + (g - g0) * 8), acc);
       if (live) {
         const int n0 = g * 8;
 #pragma unroll
@@ -400,49 +494,17 @@ __device__ __forceinline__ void tc_adam_normal(const TcRing& R, float* __restric
   }
 }
 
-// Adam epilogue of dW in the TRANSPOSED orientation: accumulator row = n (tile t, lane r), column = k; column Kuse = bias.
-__device__ __forceinline__ void tc_adam_transposed(const TcRing& R, float* __restrict__ ws, const TcLayer& Ly, int pm, int m_tiles,
-                                                   int n_cols, const TcHyper& hp) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, cg = warp >> 2;
-  const int ngroups = n_cols >> 3;
-  for (int t = 0; t < m_tiles; ++t) {
-    const int n = t * 128 + q * 32 + lane;
-    for (int g = cg; g < ngroups; g += kTCG) {
-      float acc[8];
-      if (m_tiles == 1) t_ld8_sum(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), acc);
-      else t_ld8(R.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + g * 8), acc);
-      if (n >= Ly.N) continue;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = g * 8 + j;
-        if (k > Ly.Kuse) continue;
-        float* P = k == Ly.Kuse ? ws + Ly.Bv + n : ws + Ly.W + tc_w8(Ly, k, n);
-        float m = P[pm], v = P[2 * pm];
-        const float pn = t_adam(P[0], m, v, acc[j], hp);
-        P[0] = pn; P[pm] = m; P[2 * pm] = v;
-        if (k < Ly.Kuse) ws[Ly.WT + (size_t)n * Ly.Kp + k] = pn;
-      }
-    }
-  }
-}
-
-// dW of one layer (+ Adam).  Orientation: rows = the larger of (Kuse + 1, N) so the small dimension is the MMA N.
+// dW of one layer (+ Adam) on this CTA's column groups [g0, g1): D[k][n] = sum_b X^T[k][b] dY^T[n][b], rows k incl. the
+// ones row (bias), one or two M tiles.
 __device__ __forceinline__ void tc_dw(TcRing& R, float* __restrict__ ws, const TcLayer& Ly, const CUtensorMap* lm, int BP, int pm,
-                                      const TcHyper& hp) {
+                                      int g0, int g1, const TcHyper& hp) {
+  if (g0 >= g1) return;
   const int xrows = t_up8(Ly.Kuse + 1);            // X^T rows incl. the ones row (box rows of the TM_INT map)
-  if (Ly.Kuse + 1 >= Ly.N) {                       // normal: D[k][n]
-    const int tiles = (Ly.Kuse + 1 + 127) >> 7;
-    tc_gemm(R, TcOperand{lm + TM_INT, 0, xrows}, tiles, TcOperand{lm + TM_GT, 0, Ly.Np}, Ly.Np, BP);
-    TC_T0();
-    tc_adam_normal(R, ws, Ly, pm, tiles, hp);
-    TC_ACC(2);
-  } else {                                          // transposed: D[n][k]
-    const int tiles = (Ly.N + 127) >> 7;
-    tc_gemm(R, TcOperand{lm + TM_GT, 0, Ly.Np}, tiles, TcOperand{lm + TM_INT, 0, xrows}, xrows, BP);
-    TC_T0();
-    tc_adam_transposed(R, ws, Ly, pm, tiles, xrows, hp);
-    TC_ACC(3);
-  }
+  const int tiles = (Ly.Kuse + 1 + 127) >> 7;
+  tc_gemm(R, TcOperand{lm + TM_INT, 0, xrows}, tiles, TcOperand{lm + TM_GT, 0, Ly.nbox, g0 * 8}, Ly.nbox, BP);
+  TC_T0();
+  tc_adam(R, ws, Ly, pm, tiles, g0, g1, hp);
+  TC_ACC(2);
   tc_epilogue_done();
 }
 
@@ -458,15 +520,17 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
   __shared__ uint32_t keys[8];
   __shared__ float sl_s[64], scal_s[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cg = warp >> 2;
-  const CUtensorMap* gmaps = jobs[blockIdx.x].maps;                 // TMA reads the maps from the job table itself
+  const int csize = (int)t_cluster_size(), rank = (int)t_cluster_rank();   // CTAs of this model's cluster, this CTA's place
+  const int jidx = (int)blockIdx.x / csize;
+  const CUtensorMap* gmaps = jobs[jidx].maps;                       // TMA reads the maps from the job table itself
   {
-    const int* src = reinterpret_cast<const int*>(jobs + blockIdx.x);
+    const int* src = reinterpret_cast<const int*>(jobs + jidx);
     int* dst = reinterpret_cast<int*>(&J);
     for (int i = tid; i < (int)(offsetof(TcJobDev, maps) / 4); i += kTT) dst[i] = src[i];
   }
   if (tid == 0) {
     for (int i = 0; i <= 3 * kTMaxStages; ++i)
-      t_mbar_init(&bars[i], (i >= kTMaxStages && i < 2 * kTMaxStages) ? kTW - 1 : 1);       // ready[]: one arrive per converter warp
+      t_mbar_init(&bars[i], (i >= kTMaxStages && i < 2 * kTMaxStages) ? kTW - 2 : 1);       // ready[]: one arrive per converter warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -491,7 +555,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
   for (int net = 0; net < 2; ++net)
     for (int i = 0; i < (net ? nd : ne); ++i) {
       const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
-      for (int idx = tid; idx < Ly.K * Ly.N; idx += kTT) {
+      for (int idx = rank * kTT + tid; idx < Ly.K * Ly.N; idx += csize * kTT) {
         const int k = idx / Ly.N, n = idx - k * Ly.N;
         const float p = J.params[Ly.flat_w + idx];
         const size_t o = Ly.W + tc_w8(Ly, k, n);
@@ -500,13 +564,14 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
         ws[o + 2 * pm] = J.adam_v[Ly.flat_w + idx];
         if (k < Ly.Kuse) ws[Ly.WT + (size_t)n * Ly.Kp + k] = p;
       }
-      for (int n = tid; n < Ly.N; n += kTT) {
+      for (int n = rank * kTT + tid; n < Ly.N; n += csize * kTT) {
         ws[Ly.Bv + n] = J.params[Ly.flat_b + n];
         ws[Ly.Bv + pm + n] = J.adam_m[Ly.flat_b + n];
         ws[Ly.Bv + 2 * pm + n] = J.adam_v[Ly.flat_b + n];
       }
       // the ones row of the layer input's feature-major copy: row Kuse (bias gradient = ones . dY)
-      for (int b = tid; b < BP; b += kTT) ws[Ly.in_T + (size_t)Ly.Kuse * BP + b] = b < B ? 1.0f : 0.0f;
+      if (rank == 0)
+        for (int b = tid; b < BP; b += kTT) ws[Ly.in_T + (size_t)Ly.Kuse * BP + b] = b < B ? 1.0f : 0.0f;
     }
   // Encoder layer 0 rows d >= DR multiply exactly-zero padding columns (gradient exactly 0): untouched unless the
   // caller supplied NON-zero Adam moments there, in which case they take the g = 0 Adam update every step.
@@ -526,6 +591,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
   const float invB = 1.0f / (float)B, fB = (float)B;
   const int row = q * 32 + lane;                 // accumulator row (TMEM lane) this thread drains
   const uint32_t trow = R.tmem + ((uint32_t)(q * 32) << 16);
+  const int mask_ofs = rank * BP * 8;              // this CTA's private copy of the relu masks (floats from Ly.*_mask)
   __syncthreads();
 
   for (int64_t s = 0; s < n_steps; ++s) {
@@ -554,23 +620,27 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
       const uint32_t lk0 = keys[0], lk1 = keys[1], bk0 = keys[2], bk1 = keys[3];
       const int n_e = B * LD, half_e = (n_e + 1) >> 1, n_d = B * G, half_d = (n_d + 1) >> 1;
       float* z = ws + J.ws_z; float* gn = ws + J.ws_gn;
-      for (int w = tid; w < half_e + half_d; w += kTT) {
-        if (w < half_e) {
-          const int j = w, j2 = w + half_e;
-          uint32_t x0 = (uint32_t)j, x1 = j2 < n_e ? (uint32_t)j2 : 0u;
-          threefry2x32(lk0, lk1, x0, x1);
-          z[j] = normal_from_bits(x0);
-          if (j2 < n_e) z[j2] = normal_from_bits(x1);
-        } else {
-          const int j = w - half_e, j2 = j + half_d;
-          uint32_t x0 = (uint32_t)j, x1 = j2 < n_d ? (uint32_t)j2 : 0u;
-          threefry2x32(bk0, bk1, x0, x1);
-          gn[j] = normal_from_bits(x0);
-          if (j2 < n_d) gn[j2] = normal_from_bits(x1);
-        }
+      // eps is consumed by CTA 0 only, much later: every CTA of the cluster draws a share of it.  The generator normals
+      // (few) and the batch are produced by EVERY CTA for itself -- identical values into the same global arrays -- so
+      // the first GEMM of the step waits for nobody.
+      for (int w = rank * kTT + tid; w < half_e; w += csize * kTT) {
+        const int j = w, j2 = w + half_e;
+        uint32_t x0 = (uint32_t)j, x1 = j2 < n_e ? (uint32_t)j2 : 0u;
+        threefry2x32(lk0, lk1, x0, x1);
+        z[j] = normal_from_bits(x0);
+        if (j2 < n_e) z[j2] = normal_from_bits(x1);
+      }
+      for (int w = tid; w < half_d; w += kTT) {
+        const int j = w, j2 = j + half_d;
+        uint32_t x0 = (uint32_t)j, x1 = j2 < n_d ? (uint32_t)j2 : 0u;
+        threefry2x32(bk0, bk1, x0, x1);
+        gn[j] = normal_from_bits(x0);
+        if (j2 < n_d) gn[j2] = normal_from_bits(x1);
       }
     }
-    __syncthreads();
+    // Step boundary of the cluster: every CTA has finished the previous step (its dW GEMMs read activations and
+    // gradients this step overwrites; its Adam wrote weights this step reads), and eps is complete.
+    tc_cluster_sync(csize);
     // ================= generator transform (bit-exact op order, oracle/datasets.py): x -> batch-major + feature-major
     for (int b = tid; b < B; b += kTT) {
       const float* gr = ws + J.ws_gn + (size_t)b * G;
@@ -597,6 +667,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
         xb(J.dd) = sg; xT[(size_t)J.dd * BP] = sg;
       }
     }
+    asm volatile("fence.proxy.async.global;" ::: "memory");      // the batch is read by TMA next
     __syncthreads();
 #ifdef VAE_TC_PROFILE
     if (tid == 0 && blockIdx.x == 0) g_tc_prof[6] += clock64() - _ts;
@@ -610,14 +681,17 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
         const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
         const int kpad = i == 0 ? t_up8(Ly.Kuse) : Ly.Kp;
         const CUtensorMap* lm = gmaps + (net * kTMaxL + i) * TM_PER_LAYER;
-        tc_gemm(R, TcOperand{lm + TM_INBM, 1, 128}, 1, TcOperand{lm + TM_WT, 0, Ly.Np}, Ly.Np, kpad, ws + Ly.Bv, Ly.N);
+        int g0, g1;                                      // this CTA's column groups of the layer
+        tc_slice(Ly.Np >> 3, csize, rank, &g0, &g1);
+        if (g0 < g1)
+          tc_gemm(R, TcOperand{lm + TM_INBM, 1, 128}, 1, TcOperand{lm + TM_WT, 0, Ly.nbox, g0 * 8}, Ly.nbox, kpad, ws + Ly.Bv, Ly.N);
         TC_T0();
         const float* bias = R.bias_s;
         const bool last = i == nl - 1;
         uint64_t mbits = 0;                              // relu'(output) bytes of this thread's column groups (hidden layers)
-        for (int g = cg; g < (Ly.Np >> 3); g += kTCG) {
+        for (int g = g0 + cg; g < g1; g += kTCG) {
           float acc[8];
-          t_ld8_sum(trow + (uint32_t)(g * 8), acc);
+          t_ld8_sum(trow + (uint32_t)((g - g0) * 8), acc);
           if (row >= BP) continue;
           const int n0 = g * 8;
           const bool vrow = row < B;
@@ -633,7 +707,7 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
             uint64_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) bits |= (uint64_t)(y[j] > 0.f ? 1u : 0u) << j;
-            mbits |= bits << ((g / kTCG) * 8);
+            mbits |= bits << (((g - g0) / kTCG) * 8);
           } else if (net == 0) {                         // mu; zs = mu + exp(lv/2) z1 (networks.py:67-74)
             const TcLayer& D0 = J.dec[0];
             float mu[8], zs[8];
@@ -673,13 +747,13 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
           }
         }
         if (!last && row < BP)                           // [BP][kTCG][8 bytes]: read back by the same (row, cg) thread
-          reinterpret_cast<uint2*>(ws + Ly.out_mask)[row * kTCG + cg] = make_uint2((uint32_t)mbits, (uint32_t)(mbits >> 32));
-        tc_epilogue_done();
+          reinterpret_cast<uint2*>(ws + Ly.out_mask + mask_ofs)[row * kTCG + cg] = make_uint2((uint32_t)mbits, (uint32_t)(mbits >> 32));
+        tc_cluster_sync(csize);
         TC_ACC(4);
       }
     }
     // ================= loss (networks.py:94-98) and the decoder log-variance parameter
-    {
+    if (rank == 0) {                                     // the narrow mu / x_hat layers are CTA 0's: so are all loss partials
       const float s_r2 = tc_block_sum(r2, red), s_rz = tc_block_sum(rz, red), s_mu2 = tc_block_sum(kl_part, red);
       if (tid == 0) {
         const float e = scal_s[0], sd = scal_s[1], inv_var = scal_s[2];
@@ -708,23 +782,27 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
           const bool latent = net == 1 && i == 0;       // dzs: -> d lv partials, dmu = dzs + mu / B
           uint64_t mbits = 0;                            // relu'(layer input) bytes of this thread's (row, cg) column groups
           if (!latent && row < BP) {
-            const uint2 mk = reinterpret_cast<const uint2*>(ws + Ly.in_mask)[row * kTCG + cg];
+            const uint2 mk = reinterpret_cast<const uint2*>(ws + Ly.in_mask + mask_ofs)[row * kTCG + cg];
             mbits = (uint64_t)mk.x | ((uint64_t)mk.y << 32);
           }
           const CUtensorMap* lm = gmaps + (net * kTMaxL + i) * TM_PER_LAYER;
-          tc_gemm(R, TcOperand{gmaps + 2 * kTMaxL * TM_PER_LAYER + cur, 1, 128}, 1, TcOperand{lm + TM_W8, 1, Ly.Kp}, Ly.Kp, Ly.Np);
+          int g0, g1;                                    // this CTA's groups of the layer's INPUT features (the dX columns)
+          tc_slice(Ly.Kp >> 3, csize, rank, &g0, &g1);
+          if (g0 < g1)
+            tc_gemm(R, TcOperand{gmaps + 2 * kTMaxL * TM_PER_LAYER + cur, 1, 128}, 1, TcOperand{lm + TM_W8, 1, Ly.kbox, g0 * 8}, Ly.kbox, Ly.Np);
           TC_T0();
-          float* obm = ws + J.ws_gbm[cur ^ 1];
-          float* oT = ws + J.ws_gT[cur ^ 1];
-          for (int g = cg; g < (Ly.Kp >> 3); g += kTCG) {
+          const int nxt = cur + 1 == kTGradBufs ? 0 : cur + 1;
+          float* obm = ws + J.ws_gbm[nxt];
+          float* oT = ws + J.ws_gT[nxt];
+          for (int g = g0 + cg; g < g1; g += kTCG) {
             float acc[8];
-            t_ld8_sum(trow + (uint32_t)(g * 8), acc);
+            t_ld8_sum(trow + (uint32_t)((g - g0) * 8), acc);
             const int k0 = g * 8;
             const bool vrow = row < B;
             const size_t gofs = ((size_t)g * BP + (row < BP ? row : 0)) * 8;
             float o[8];
             if (!latent) {
-              const uint32_t bits = (uint32_t)(mbits >> ((g / kTCG) * 8)) & 0xFFu;
+              const uint32_t bits = (uint32_t)(mbits >> (((g - g0) / kTCG) * 8)) & 0xFFu;
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = (vrow && ((bits >> j) & 1u)) ? acc[j] : 0.f;
             } else {
@@ -750,9 +828,9 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
                 if (k0 + j < Ly.K) oT[(size_t)(k0 + j) * BP + row] = o[j];
             }
           }
-          tc_epilogue_done();
+          tc_cluster_sync(csize);
           TC_ACC(5);
-          if (latent && tid < L) {          // g_lv[l] = sum_b dzs z1 * 0.5 s_l - 0.5 (1 - e^lv_l)
+          if (latent && rank == 0 && tid < L) {          // g_lv[l] = sum_b dzs z1 * 0.5 s_l - 0.5 (1 - e^lv_l)
             const int gsel = (tid >> 3) % kTCG;   // column group g was drained by the four warps with cg == g % kTCG
             float a = 0.f;
             for (int w = 0; w < 4; ++w) a += lvred[4 * gsel + w][tid];
@@ -762,12 +840,16 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
             J.adam_m[J.off_lv + tid] = m; J.adam_v[J.off_lv + tid] = v;
           }
         }
-        tc_dw(R, ws, Ly, gmaps + (net * kTMaxL + i) * TM_PER_LAYER, BP, pm, hp);
-        cur ^= need_dx ? 1 : 0;
+        {
+          int g0, g1;
+          tc_slice(Ly.Np >> 3, csize, rank, &g0, &g1);
+          tc_dw(R, ws, Ly, gmaps + (net * kTMaxL + i) * TM_PER_LAYER, BP, pm, g0, g1, hp);
+        }
+        if (need_dx) cur = cur + 1 == kTGradBufs ? 0 : cur + 1;
       }
     }
     if (decay_skipped) {
-      for (int idx = tid; idx < (E0.K - DR) * E0.N; idx += kTT) {
+      for (int idx = rank * kTT + tid; idx < (E0.K - DR) * E0.N; idx += csize * kTT) {
         float* P = ws + E0.W + tc_w8(E0, DR + idx / E0.N, idx % E0.N);
         float m = P[pm], v = P[2 * pm];
         P[0] = t_adam(P[0], m, v, 0.f, hp); P[pm] = m; P[2 * pm] = v;
@@ -779,25 +861,26 @@ fused_mlp_tc_kernel(const TcJobDev* __restrict__ jobs, int64_t n_steps) {
 #endif
   }
 
-  // ---- aligned copies -> flat (C ABI) vectors
+  // ---- aligned copies -> flat (C ABI) vectors (every CTA of the cluster takes a share, once all Adam updates are in)
+  tc_cluster_sync(csize);
   for (int net = 0; net < 2; ++net)
     for (int i = 0; i < (net ? nd : ne); ++i) {
       const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
-      for (int idx = tid; idx < Ly.K * Ly.N; idx += kTT) {
+      for (int idx = rank * kTT + tid; idx < Ly.K * Ly.N; idx += csize * kTT) {
         const int k = idx / Ly.N, n = idx - k * Ly.N;
         const size_t o = Ly.W + tc_w8(Ly, k, n);
         J.params[Ly.flat_w + idx] = ws[o];
         J.adam_m[Ly.flat_w + idx] = ws[o + pm];
         J.adam_v[Ly.flat_w + idx] = ws[o + 2 * pm];
       }
-      for (int n = tid; n < Ly.N; n += kTT) {
+      for (int n = rank * kTT + tid; n < Ly.N; n += csize * kTT) {
         J.params[Ly.flat_b + n] = ws[Ly.Bv + n];
         J.adam_m[Ly.flat_b + n] = ws[Ly.Bv + pm + n];
         J.adam_v[Ly.flat_b + n] = ws[Ly.Bv + 2 * pm + n];
       }
     }
-  if (tid == 0) J.step[0] = step0 + (int32_t)n_steps;
-  if (tid < 4 && (tid & 1) == 0) { uint32_t* dst = tid < 2 ? J.model_key : J.dataset_key; dst[0] = ck0; dst[1] = ck1; }
+  if (rank == 0 && tid == 0) J.step[0] = step0 + (int32_t)n_steps;
+  if (rank == 0 && tid < 4 && (tid & 1) == 0) { uint32_t* dst = tid < 2 ? J.model_key : J.dataset_key; dst[0] = ck0; dst[1] = ck1; }
   t_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(R.tmem));
@@ -848,7 +931,7 @@ static int tc_make_map(CUtensorMap* tm, const float* ptr, int grouped, int rows,
 
 // Workspace layout (floats).  Every offset is a multiple of 8 floats; every row stride a multiple of 8.  The caller
 // zero-fills the workspace once (padding rows / columns are never written).
-static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
+static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o, int csize) {
   Layout Lo;
   if (make_layout(&j.desc, &Lo)) return 0;
   const VaeDesc& d = j.desc;
@@ -863,7 +946,7 @@ static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
   J.B = B; J.BP = BP; J.D = D; J.L = L; J.DR = DR; J.kind = g.kind; J.G = G; J.dd = g.dim;
   J.tunable = d.tunable_decoder_var; J.n_enc = Lo.n_enc; J.n_dec = Lo.n_dec;
   J.Lp = t_up8(L); J.Dp = t_up8(D); J.LD = L + D;
-  J.off_lv = (int32_t)Lo.off_eps_p; J.off_eps = (int32_t)Lo.off_eps; J.n_flat = (int32_t)Lo.n_params;
+  J.off_lv = (int32_t)Lo.off_eps_p; J.off_eps = (int32_t)Lo.off_eps; J.n_flat = (int32_t)Lo.n_params; J.csize = csize;
   int maxw = 8;
   // aligned parameter region P; M and V repeat it pm_stride floats further
   for (int net = 0; net < 2; ++net)
@@ -872,6 +955,7 @@ static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
       const int* sz = net ? Lo.dec_sizes : Lo.enc_sizes;
       Ly.K = sz[i]; Ly.N = sz[i + 1]; Ly.Kp = t_up8(Ly.K); Ly.Np = t_up8(Ly.N);
       Ly.Kuse = (net == 0 && i == 0) ? DR : Ly.K;
+      Ly.nbox = tc_slice_box(Ly.Np >> 3, csize); Ly.kbox = tc_slice_box(Ly.Kp >> 3, csize);
       Ly.flat_w = (int32_t)(net ? Lo.dec_w[i] : Lo.enc_w[i]); Ly.flat_b = (int32_t)(net ? Lo.dec_b[i] : Lo.enc_b[i]);
       Ly.W = take((size_t)Ly.K * Ly.Np); Ly.Bv = take(Ly.Np);
       if (Ly.Kp > maxw) maxw = Ly.Kp;
@@ -895,21 +979,22 @@ static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
       TcLayer& Ly = net ? J.dec[i] : J.enc[i];
       TcLayer& Nx = net ? J.dec[i + 1] : J.enc[i + 1];
       Ly.out_bm = Nx.in_bm; Ly.out_T = Nx.in_T;
-      Ly.out_mask = take((size_t)BP * 8);               // [BP][32] bytes
+      Ly.out_mask = take((size_t)BP * 8 * kTMaxCluster);   // [cluster rank][BP][32] bytes
       Nx.in_mask = Ly.out_mask;
     }
   }
   J.ws_z = take((size_t)BP * (L + D) + 8); J.ws_gn = take((size_t)BP * G + 8); J.ws_mu = take((size_t)BP * J.Lp);
-  for (int b = 0; b < 2; ++b) { J.ws_gbm[b] = take((size_t)BP * maxw); J.ws_gT[b] = take((size_t)(maxw + 8) * BP); }
+  for (int b = 0; b < kTGradBufs; ++b) { J.ws_gbm[b] = take((size_t)BP * maxw); J.ws_gT[b] = take((size_t)(maxw + 8) * BP); }
   // which gradient buffer holds each layer's dY: the backward pass walks dec[nd-1] .. dec[0], enc[ne-1] .. enc[0]
-  // and flips after every layer that produces a dX
+  // and moves on after every layer that produces a dX.  Three buffers in rotation: in a cluster, layer i - 1's dX
+  // (written two buffers on) must not land on the dY a slower peer's dW of layer i is still reading.
   {
     int cur = 0;
     for (int net = 1; net >= 0; --net)
       for (int i = (net ? Lo.n_dec : Lo.n_enc) - 1; i >= 0; --i) {
         TcLayer& Ly = net ? J.dec[i] : J.enc[i];
         Ly.gcur = cur;
-        if (!(net == 0 && i == 0)) cur ^= 1;
+        if (!(net == 0 && i == 0)) cur = (cur + 1) % kTGradBufs;
       }
   }
   if (o) {
@@ -919,14 +1004,14 @@ static size_t tc_fill(const VaeTrainJob& j, TcJobDev* o) {
         const TcLayer& Ly = net ? J.dec[i] : J.enc[i];
         CUtensorMap* lm = J.maps + (net * kTMaxL + i) * TM_PER_LAYER;
         const int xrows = t_up8(Ly.Kuse + 1);
-        if (tc_make_map(lm + TM_WT, wsb + Ly.WT, 0, Ly.Np, Ly.Kp, Ly.Kp, Ly.Np) ||                 // B of the forward GEMM
-            tc_make_map(lm + TM_W8, wsb + Ly.W, 1, Ly.K, Ly.Np, Ly.K, Ly.Kp) ||                   // B of dX: rows k, K = n
+        if (tc_make_map(lm + TM_WT, wsb + Ly.WT, 0, Ly.Np, Ly.Kp, Ly.Kp, Ly.nbox) ||               // B of the forward GEMM (row slice)
+            tc_make_map(lm + TM_W8, wsb + Ly.W, 1, Ly.K, Ly.Np, Ly.K, Ly.kbox) ||                 // B of dX: rows k (slice), K = n
             tc_make_map(lm + TM_INBM, wsb + Ly.in_bm, 1, BP, Ly.Kp, BP, 128) ||                   // A of the forward GEMM
             tc_make_map(lm + TM_INT, wsb + Ly.in_T, 0, xrows, BP, BP, xrows) ||                   // X^T (+ ones row) of dW
-            tc_make_map(lm + TM_GT, wsb + J.ws_gT[Ly.gcur], 0, Ly.Np, BP, BP, Ly.Np))             // dY^T of dW
+            tc_make_map(lm + TM_GT, wsb + J.ws_gT[Ly.gcur], 0, Ly.Np, BP, BP, Ly.nbox))           // dY^T of dW (row slice)
           return 0;
       }
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < kTGradBufs; ++b)
       if (tc_make_map(J.maps + 2 * kTMaxL * TM_PER_LAYER + b, wsb + J.ws_gbm[b], 1, BP, maxw, BP, 128)) return 0;   // A of dX
     *o = J;
     o->params = j.params; o->adam_m = j.adam_m; o->adam_v = j.adam_v; o->step = j.step;
@@ -949,17 +1034,41 @@ int mlp_tc_supported(const VaeTrainJob* j, size_t* ws_bytes) {
   const int width = g.dim + g.padding_dim;
   if (width != d.data_dim || d.latent_dim > 63 || d.batch > 128 || d.batch < 1) return 0;
   if (Lo.max_width > kTMaxN - 8 || Lo.n_params >= (1ll << 30)) return 0;      // N <= 208 incl. the bias column / row
-  if (ws_bytes) *ws_bytes = tc_fill(*j, nullptr) * sizeof(float);
+  if (ws_bytes) *ws_bytes = tc_fill(*j, nullptr, 1) * sizeof(float);      // the layout does not depend on the cluster size
   return 1;
 }
 
 size_t mlp_tc_job_bytes() { return sizeof(TcJobDev); }
 
-int mlp_tc_fill_job(const VaeTrainJob& j, void* out) {
-  return tc_fill(j, (TcJobDev*)out) ? 0 : VAE_ERR_INVALID;
+int mlp_tc_fill_job(const VaeTrainJob& j, void* out, int csize) {
+  return tc_fill(j, (TcJobDev*)out, csize) ? 0 : VAE_ERR_INVALID;
 }
 
-int mlp_tc_prepare() {
+// Clusters of `cs` CTAs of the kernel that can be co-resident on the device (one CTA per SM).
+static int tc_active_clusters(int cs, int* out) {
+  if (cs == 1) {
+    int dev = 0, sms = 0;
+    VAE_CUDA_OK(cudaGetDevice(&dev));
+    VAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *out = sms;
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cs, 1, 1);
+  cfg.blockDim = dim3(kTT, 1, 1);
+  cfg.dynamicSmemBytes = kTSmemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  VAE_CUDA_OK(cudaOccupancyMaxActiveClusters(out, fused_mlp_tc_kernel, &cfg));
+  return 0;
+}
+
+// Sets the kernel's shared-memory attribute and picks the cluster size for a pack of n_jobs models: the largest of
+// 8 / 4 / 2 CTAs per model that keeps the whole pack resident (latency), else one CTA per model (throughput).
+// VAE_MLP_TC_CLUSTER=1|2|4|8 forces a size (A/B runs).
+int mlp_tc_prepare(int n_jobs, int* cluster) {
   cudaFuncAttributes fa;
   VAE_CUDA_OK(cudaFuncGetAttributes(&fa, fused_mlp_tc_kernel));
   VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -968,12 +1077,35 @@ int mlp_tc_prepare() {
     set_error("fused_mlp_tc_kernel needs %zu bytes of shared memory", (size_t)kTSmemBytes + fa.sharedSizeBytes);
     return VAE_ERR_INVALID;
   }
+  int cs = 1;
+  const char* e = getenv("VAE_MLP_TC_CLUSTER");
+  if (e && e[0]) {
+    const int v = atoi(e);
+    cs = v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
+  } else {
+    for (int c = kTMaxCluster; c > 1; c >>= 1) {
+      int fit = 0;
+      if (tc_active_clusters(c, &fit) != 0) { cudaGetLastError(); continue; }
+      if (n_jobs <= fit) { cs = c; break; }
+    }
+  }
+  *cluster = cs;
   return 0;
 }
 
 int mlp_tc_launch(const VaePackPlan* plan, int64_t n_steps, cudaStream_t s) {
-  fused_mlp_tc_kernel<<<plan->n_jobs, kTT, kTSmemBytes, s>>>((const TcJobDev*)plan->d_jobs, n_steps);
-  VAE_LAUNCH_OK("fused_mlp_tc_kernel");
+  const int cs = plan->cluster < 1 ? 1 : plan->cluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(plan->n_jobs * cs), 1, 1);
+  cfg.blockDim = dim3(kTT, 1, 1);
+  cfg.dynamicSmemBytes = kTSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = cs > 1 ? 1 : 0;
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, fused_mlp_tc_kernel, (const TcJobDev*)plan->d_jobs, n_steps));
+  count_launch();
   return 0;
 }
 
