@@ -438,7 +438,7 @@ def measure_sweep_mix(ctx, K, W, peak):
     from vae_training_b200.vae import _parse_sizes
     torch = ctx.torch
     all_args = sweep.builtin_runs("all")
-    mine = sweep.lpt_partition([sweep.run_cost(a) for a in all_args], ctx.world)[ctx.rank]
+    mine = sweep.latency_partition(all_args, ctx.world)[ctx.rank]
     specs = [RunSpec(dataset=a.dataset, dataset_dimension=a.dataset_dimension, padding_dim=a.padding_dim,
                      latent_dimension=a.latent_dimension, layer_sizes=_parse_sizes(a.layer_sizes),
                      encoder_layer_sizes=_parse_sizes(a.encoder_layer_sizes), batch_size=a.batch_size,
@@ -486,7 +486,7 @@ def measure_sweep_mix(ctx, K, W, peak):
             "config": {"workload": "all 54 runs of seed_linpadding_expts.sh, sigmoid_vae_padding_expts.sh, "
                                    "sphere_vae_padding_expts.sh advanced K steps together (BASELINE.json configs[3]); "
                                    "one single-Dense pack + one hidden-layer pack on two streams per GPU",
-                       "parallelism": f"LPT partition over {ctx.world} GPU(s), no collective"}}
+                       "parallelism": f"latency-aware partition (sweep.latency_partition) over {ctx.world} GPU(s), no collective"}}
 
 
 def measure_dp(ctx, workload, K, W):

@@ -49,6 +49,13 @@ RUNS = {
     "ref_linear_noise_dn": ["lin_noise", "--dataset", "linear_gaussian", "--encoder_layer_sizes", "", "--layer_sizes", "",
                             "-ow", "--latent_dim", "5", "--padding_dim", "2", "-dd", "4", "--num_batches", "60",
                             "--epsilon", "-1", "-tdv", "-ds", "3", "-lr", "1e-3", "-dn", "0.25"],
+    # warm start (-ws, vae.py:61-103): the hand-built starting point + perturbations drawn with the carried model key
+    "ref_sigmoid_warm_start": ["sig_ws", "--dataset", "sigmoid", "--encoder_layer_sizes", "", "--layer_sizes", "", "-ow",
+                               "--latent_dim", "6", "--padding_dim", "2", "-dd", "3", "--num_batches", "40", "--epsilon", "-3",
+                               "-tdv", "-ws"],
+    "ref_linear_warm_start": ["lin_ws", "--dataset", "linear_gaussian", "--encoder_layer_sizes", "", "--layer_sizes", "",
+                              "-ow", "--latent_dim", "8", "--padding_dim", "3", "-dd", "3", "--num_batches", "40",
+                              "--epsilon", "-1", "-tdv", "-ds", "2", "-lr", "1e-3", "-ws", "-off", "1"],
 }
 
 

@@ -9,7 +9,26 @@ from . import nn  # noqa: F401
 from . import lax  # noqa: F401
 from . import scipy  # noqa: F401
 
-ops = None          # jax.ops.index_update: warm start only (vae.py:62-107), never enabled by the scripts
+
+
+class _Index:
+    """jax.ops.index[...]: the index expression itself."""
+    def __getitem__(self, idx):
+        return idx
+
+
+class _Ops:
+    """jax.ops.index_update / jax.ops.index (legacy JAX; warm start only, vae.py:62-107): functional x[idx] = y."""
+    index = _Index()
+
+    @staticmethod
+    def index_update(x, idx, y):
+        out = x.clone()
+        out[idx] = y
+        return out
+
+
+ops = _Ops()
 
 
 def jit(fn=None, **_kw):

@@ -203,3 +203,25 @@ def test_all_54_sweep_runs_short_match_oracle(monkeypatch):
     for m, (tr, ods_) in zip(models, trainers):
         tr.train(N)
         compare(m, tr, ods_, N)
+
+
+def test_gaussian_dataset_batches_and_scores():
+    """datasets.py:101-160 (constructed directly; run.py never selects it): (size, dim + padding) batches from two
+    key-chain draws (normal part, N(0, noise_level) padding) bit-identical to the jax.random restatement, and the
+    reference's three score entries."""
+    from oracle import jax_random as jr
+    from vae_training_b200 import datasets
+    ds = datasets.GaussianDataset(5, dimension=3, padding_dimension=2, noise_level=0.04)
+    key = jr.PRNGKey(5)
+    key, k1 = jr.split(key)
+    key, k2 = jr.split(key)
+    ref = np.concatenate([jr.normal(k1, (64, 3)), jr.normal(k2, (64, 2)) * np.float32(np.sqrt(np.float32(0.04)))], axis=1)
+    got = ds.get_batch(64)
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.uint32), ref.astype(np.float32).view(np.uint32))
+    np.testing.assert_array_equal(ds.key.cpu().numpy(), key)
+    sc = ds.score_batch(got)
+    assert set(sc) == {"Squared Norm of padding dimensions", "ground truth eigenvalue", "learnt eigenvalue"}
+    assert abs(float(sc["Squared Norm of padding dimensions"]) - float((ref[:, 3:] ** 2).sum(1).mean())) < 1e-6
+    assert sc["learnt eigenvalue"].shape == (5,)
+    z = datasets.GaussianDataset(5, dimension=3, padding_dimension=2, noise_level=0.0).get_batch(8)
+    assert float(z[:, 3:].abs().max()) == 0.0

@@ -46,6 +46,22 @@ def test_lpt_partition_balances_and_covers():
     assert sweep.lpt_partition([3.0, 1.0], 1) == [[0, 1]]
 
 
+def test_latency_partition_spreads_the_hidden_layer_chains():
+    """The 54 runs over 8 GPUs: the 15 sphere chains (150 000 serial steps each -- the wall time) go two per GPU, the 39
+    single-Dense runs are spread beside them; every run lands on exactly one rank for every world size."""
+    runs = sweep.builtin_runs("all")
+    for world in (1, 2, 3, 4, 8):
+        parts = sweep.latency_partition(runs, world)
+        assert sorted(sum(parts, [])) == list(range(len(runs)))
+        sph = [sum(1 for i in p if runs[i].dataset == "sphere") for p in parts]
+        assert max(sph) - min(sph) <= 1
+        small = [len(p) - s for p, s in zip(parts, sph)]
+        assert max(small) - min(small) <= 3
+    parts = sweep.latency_partition(runs, 8)
+    assert max(sweep.estimated_wall_seconds(runs, p) for p in parts) <= 150000 * 150e-6 + 1e-9     # one 16-CTA chain latency
+    assert sweep.chain_latency_us(1) < sweep.chain_latency_us(15) < sweep.chain_latency_us(33) < sweep.chain_latency_us(148)
+
+
 def test_runspec_shapes_match_survey_appendix_c():
     s = RunSpec("sigmoid", 7, 20, 24, tunable_decoder_var=True)
     assert s.data_dim == 28 and s.flops_per_step() == 1075200 and s.normals_per_step() == 5900

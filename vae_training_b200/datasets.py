@@ -108,6 +108,41 @@ class LinearGaussianDataset(DistributionDataset):
         return {"Squared Norm of padding dimensions": self._scores(batch)[0]}
 
 
+class GaussianDataset(DistributionDataset):
+    """datasets.py:101-160 (not reachable from run.py's --dataset choices; kept for callers that construct it
+    directly).  A standard normal in `dimension` coordinates, padding drawn N(0, noise_level I) (or zeros).  It has no
+    fused generator: batches are composed from ``ops.random_normal`` draws, so a VAEModel on it trains per-op."""
+    name = "gaussian"
+
+    def __init__(self, seed, dimension=3, padding_dimension=0, noise_level=0.01, device="cuda"):
+        super().__init__(seed, device)
+        self.dim = dimension
+        self.padding_dim = padding_dimension
+        self.ndim = dimension + padding_dimension
+        self.noise_level = noise_level
+
+    def data_desc(self):
+        raise _lib.VaeB200Error("GaussianDataset has no on-device generator description (per-op batches only)")
+
+    def get_batch(self, size, return_latents=False):
+        norm = ops.random_normal(self.get_key(), (size, self.dim))
+        if self.noise_level > 0:
+            # random.multivariate_normal(key, 0, noise_level I): cholesky(cov) @ normal(key, (size, pad))
+            pad = ops.random_normal(self.get_key(), (size, self.padding_dim)) * float(np.sqrt(np.float32(self.noise_level)))
+        else:
+            pad = torch.zeros((size, self.padding_dim), dtype=torch.float32, device=self.device)
+        samps = torch.cat([norm, pad], dim=1)
+        return (samps, None) if return_latents else samps
+
+    def score_batch(self, batch):
+        padding = batch[:, self.dim:]
+        mse = (padding * padding).sum(dim=1).mean()
+        w_ht = torch.linalg.eigvalsh(torch.cov(batch.T))
+        self.get_batch(batch.shape[0])                       # datasets.py:117 draws a comparison batch from the chain
+        return {"Squared Norm of padding dimensions": mse, "ground truth eigenvalue": torch.ones_like(w_ht),
+                "learnt eigenvalue": w_ht}
+
+
 class SigmoidDataset(DistributionDataset):
     """datasets.py:230-279."""
     name = "sigmoid"

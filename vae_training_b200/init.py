@@ -1,5 +1,6 @@
 """Initial state of a run: parameter init and the PRNG key chains up to the first training
-step, computed with the library's own device RNG (no host re-implementation).
+step.  Key chains, generator matrices and the warm-start perturbations come from the library's device RNG
+(bit-identical to jax.random); the random Dense kernels are drawn on the host with NumPy (see below).
 
 Parameter init follows the *distribution* legacy flax uses (vae.py:57-60; SURVEY.md
 Appendix D): Dense kernels lecun-normal (normal truncated at +-2 sigma, variance
@@ -54,6 +55,67 @@ def init_params(spec: RunSpec, vae_key: np.ndarray) -> np.ndarray:
         else:
             parts.append(np.ones(n, np.float32))
     return np.concatenate(parts)
+
+
+def apply_warm_start(spec: RunSpec, params: np.ndarray, key: torch.Tensor, A: Optional[torch.Tensor],
+                     latent_off_dimension: int = 0) -> np.ndarray:
+    """``warm_start=True`` (vae.py:61-103): overwrite the single-Dense encoder / decoder kernels and ``epsilon_p`` of
+    freshly initialised parameters with the reference's hand-built starting point plus small normal perturbations.
+    Every perturbation is ``random.normal(self.key, shape)`` with the SAME carried model key (the reference does not
+    split it), drawn here with the device RNG; ``key`` is not advanced.  Sphere runs are left unchanged, as in the
+    reference.  Shapes the reference's own concatenations cannot produce raise ValueError."""
+    if spec.dataset not in ("sigmoid", "linear_gaussian"):
+        return params
+    if spec.layer_sizes or spec.encoder_layer_sizes:
+        raise ValueError("warm start sets Encoder/FC0 and Decoder/FC0 as (D, L) / (L, D) kernels: no hidden layers (vae.py:75-82)")
+    L, D, dd = spec.latent_dimension, spec.data_dim, spec.dataset_dimension
+    out = np.array(params, np.float32, copy=True)
+    offs, o = {}, 0
+    for name, shape in layer_shapes(spec):
+        offs[name] = (o, shape)
+        o += int(np.prod(shape))
+
+    def put(name, value):
+        off, shape = offs[name]
+        value = np.asarray(value, np.float32)
+        if value.shape != tuple(shape):
+            raise ValueError(f"warm start: {name} would get shape {value.shape}, the model has {tuple(shape)}")
+        out[off:off + value.size] = value.reshape(-1)
+
+    def normal(shape):
+        return ops.random_normal(key, shape).cpu().numpy()
+
+    if spec.dataset == "sigmoid":                                    # vae.py:62-82
+        if L != D:
+            raise ValueError("warm start (sigmoid) needs latent_dimension == dataset.dimension (vae.py:63)")
+        eye = np.eye(L, dtype=np.float32)
+        eye[dd + 1:, dd + 1:] = 0.0
+        enc_var = np.zeros(L, np.float32)
+        enc_var[dd + 1:] = -3.0
+        put("Decoder/FC0/kernel", eye + normal((L, D)) * np.float32(0.1))
+        put("SigDecoder/FC0/kernel", normal((L, D)) * np.float32(0.1))
+        put("epsilon_p", enc_var + normal((L,)) * np.float32(0.1))
+        put("Encoder/FC0/kernel", eye + normal((D, L)) * np.float32(0.1))
+    else:                                                            # vae.py:84-103
+        if not dd + latent_off_dimension < L:
+            raise ValueError("warm start (linear_gaussian) needs dataset.dim + latent_off_dimension < latent_dimension (vae.py:85)")
+        Ah = A.cpu().numpy().astype(np.float32)                      # (dim, intrinsic_dim)
+        extra = normal((dd, latent_off_dimension))
+        dec = np.concatenate([Ah, extra, np.zeros((dd, L - dd - latent_off_dimension), np.float32)], axis=1)
+        dec = np.concatenate([dec, np.zeros((D - dd, L), np.float32)], axis=0)
+        if dec.shape != (D, L):
+            raise ValueError(f"warm start: decoder constant has shape {dec.shape}, not {(D, L)} (needs intrinsic_dim == dim)")
+        dec = dec + normal((D, L)) * np.float32(0.01)
+        put("Decoder/FC0/kernel", dec.T)
+        enc = np.linalg.pinv(Ah).astype(np.float32)                  # (intrinsic_dim, dim)
+        enc = np.concatenate([enc, np.zeros((L - dd, dd), np.float32)], axis=0)
+        enc = np.concatenate([enc, np.zeros((L, D - dd), np.float32)], axis=1)
+        enc = enc + normal((L, D)) * np.float32(0.01)
+        put("Encoder/FC0/kernel", enc.T)
+        enc_var = np.zeros(L, np.float32)
+        enc_var[:Ah.shape[1] + latent_off_dimension] = -3.0
+        put("epsilon_p", enc_var + normal((L,)) * np.float32(0.1))
+    return out
 
 
 def dataset_ctor(spec: RunSpec, device="cuda") -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

@@ -39,8 +39,6 @@ class VAEModel:
                  encoder_layer_sizes, state_dict, data_fn, epsilon, tqdm, dataset, latent_dimension,
                  tunable_decoder_var=False, warm_start=False, dataset_name=None, latent_off_dimension=0,
                  initial_params: Optional[np.ndarray] = None, device="cuda", verbose=True):
-        if warm_start:
-            raise VaeB200Error("warm start (vae.py:62-107) is out of scope (SURVEY.md 8f.4)")
         self.dirname = dirname
         self.num_batches = num_batches
         self.num_epochs = num_epochs
@@ -77,6 +75,8 @@ class VAEModel:
         self.vae_key = sp[0].cpu().numpy()
         self.key.copy_(sp[1])
         params = init.init_params(self.spec, self.vae_key) if initial_params is None else np.asarray(initial_params, np.float32)
+        if warm_start:                                            # vae.py:61-103 (perturbations drawn with the carried key)
+            params = init.apply_warm_start(self.spec, params, self.key, dataset.A, latent_off_dimension)
         n = ops.param_count(self.desc)
         if params.shape != (n,):
             raise VaeB200Error(f"initial_params must have shape ({n},)")
