@@ -49,10 +49,11 @@ __host__ __device__ inline int m_batch_stride(int B) { int g = (B + 3) / 4; g |=
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-// All threads of all CTAs of the cluster.  release/acquire at cluster scope + a device fence:
-// global writes made before the barrier are visible to every CTA of the cluster after it.
+// All threads of all CTAs of the cluster.  The arrive's release and the wait's acquire are cluster-scope: every
+// thread's global writes before the barrier are visible to every thread of the cluster after it (the exchange buffers
+// are read with .cg loads / cp.async.cg, i.e. from L2).  A device-scope __threadfence() in front of it is redundant
+// and cost 3 us per step (measured 147.5 -> 144.4 us, results bit-identical).
 __device__ __forceinline__ void cluster_barrier() {
-  __threadfence();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
