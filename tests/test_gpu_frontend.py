@@ -225,3 +225,43 @@ def test_gaussian_dataset_batches_and_scores():
     assert sc["learnt eigenvalue"].shape == (5,)
     z = datasets.GaussianDataset(5, dimension=3, padding_dimension=2, noise_level=0.0).get_batch(8)
     assert float(z[:, 3:].abs().max()) == 0.0
+
+
+def test_overlapped_pack_matches_single_pack():
+    """packed.OverlappedPack (the end-to-end call of bench.py: sub-packs on their own streams, copies under compute,
+    CUDA-graph replay) against one PackedRuns over the same runs: first-round losses and final host state bit-identical
+    for eager, captured and pipelined-rounds execution; R pipelined rounds == R consecutive train_host calls."""
+    import bench
+    from vae_training_b200 import init
+    from vae_training_b200.packed import OverlappedPack, PackedRuns
+    K, R = 6, 3
+    specs = bench.make_specs("sigmoid_dd3_pd3_ld6", 24)
+    states = [init.initial_state(s) for s in specs]
+    ref = PackedRuns(specs, max_chunk=K)
+    ref_states = [init.initial_state(s) for s in specs]
+    for _ in range(R):
+        ref.train_host(ref_states, K)
+    ref_first = np.stack([st.losses[0] for st in ref_states])
+    ref_last = np.stack([st.losses[-1] for st in ref_states])
+    for mode in ("joined", "rounds"):
+        op = OverlappedPack(specs, max_chunk=K, parts=3)
+        assert [hi - lo for lo, hi in op.bounds] == [8, 8, 8]
+        op.prepare()
+        for attempt in range(3):                 # eager, capture + replay, replay
+            op.stage(states)
+            if mode == "joined":
+                op.train_host_all(K)
+                torch.cuda.synchronize()
+                np.testing.assert_array_equal(op.host_losses(K), ref_first)
+            else:
+                op.train_host_rounds(K, R)
+                torch.cuda.synchronize()
+                np.testing.assert_array_equal(op.host_losses(K), ref_last)
+                out = [init.initial_state(s) for s in specs]
+                for (lo, hi), p in zip(op.bounds, op.packs):
+                    p.unpack(out[lo:hi], K)
+                for a, b in zip(out, ref_states):
+                    np.testing.assert_array_equal(a.params, b.params)
+                    np.testing.assert_array_equal(a.model_key, b.model_key)
+                    np.testing.assert_array_equal(a.dataset_key, b.dataset_key)
+                    assert a.step == b.step == K * R
