@@ -266,6 +266,12 @@ int vae_transpose_split_tf32(const float* d_x, int64_t ldx, float* d_hiT, float*
 int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const float* d_Al, int64_t lda,
                        const float* d_Bh, const float* d_Bl, int64_t ldb, float* d_C, int64_t ldc,
                        const float* d_bias, const float* d_mask, int64_t ldm, int32_t flags, void* stream);
+/* C[M,N] = At[K,M]^T * Bt[K,N]: both operands K-row-major (M- / N-contiguous), read through MN-major tcgen05
+ * descriptors (TMA SWIZZLE_128B_ATOM_32B boxes).  This is dW = X^T dY (the transposes XLA inserts for
+ * flax.nn.Dense's kernel gradient, networks.py:99) taken straight from the batch-major split activations and
+ * gradients: At = split(X) (K = batch rows), Bt = split(dY).  lda, ldb multiples of 4 floats. */
+int vae_gemm_tn_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ath, const float* d_Atl, int64_t lda,
+                       const float* d_Bth, const float* d_Btl, int64_t ldb, float* d_C, int64_t ldc, void* stream);
 
 /* ----------------------------------------------------------------------- misc */
 const char* vae_last_error(void);

@@ -54,3 +54,25 @@ def test_gemm_epilogue_bias_relu_mask(ops):
     assert float((got.double() - torch.relu(ref + bias.double())).abs().max()) <= 1e-4
     got = ops.gemm_nt_3xtf32(Ah, Al, Bh, Bl, mask=mask)
     assert float((got.double() - ref * (mask > 0)).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 96), (300, 200, 100), (512, 1024, 4096),
+                                   (4096, 256, 8192), (1028, 132, 1000)])
+@pytest.mark.parametrize("cluster", ["2", "1"])
+def test_gemm_tn_3xtf32_matches_float64(ops, M, N, K, cluster, monkeypatch):
+    """The dW form: C = At^T Bt with both operands K-row-major, read MN-major by the tensor core from TMA
+    SWIZZLE_128B_ATOM_32B boxes (ragged M / N / K: out-of-range columns and rows are zero-filled)."""
+    monkeypatch.setenv("VAE_TC_CLUSTER", cluster)
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 11 + K)
+    At = torch.randn(K, M, device="cuda", generator=g)
+    Bt = torch.randn(K, N, device="cuda", generator=g)
+    Ah, Al = ops.split_tf32(At)
+    Bh, Bl = ops.split_tf32(Bt)
+    C = ops.gemm_tn_3xtf32(Ah, Al, Bh, Bl)
+    torch.cuda.synchronize()
+    ref = At.double().t() @ Bt.double()
+    scale = float(ref.abs().max())
+    err = float((C.double() - ref).abs().max()) / scale
+    err32 = float(((At.t() @ Bt).double() - ref).abs().max()) / scale
+    assert err <= 1.5e-6, (err, err32)
+    assert err <= 4 * err32 + 1e-7, (err, err32)

@@ -143,3 +143,32 @@ def test_mn_major_tf32_needs_the_32b_base_swizzle(lib):
     assert relerr(good, ref) <= 2e-6
     bad = run(lib, sw128_image(A), sw128_image(W), ka, mn(k * 128, 1024, 2), idesc(n, b_mn=True), 4, 32, 1024, n)
     assert np.count_nonzero(bad) == 0
+
+
+def base32_image(mat):
+    """MN-major image for kind::tf32: mat[k][mn] (k rows, mn % 32 == 0) -> for each 32-wide mn block a [k][128 B] tile whose
+    32-byte chunk index is XOR-ed with (k % 4)  (= TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B of a {32, k} box)."""
+    rows, cols = mat.shape
+    img = np.zeros((cols // 32, rows, 4, 8), np.float32)
+    for a in range(cols // 32):
+        blk = mat[:, 32 * a:32 * a + 32].reshape(rows, 4, 8)
+        for r in range(rows):
+            img[a, r][np.arange(4) ^ (r % 4)] = blk[r]
+    return img.reshape(-1)
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_mn_major_a_and_b_base32(lib, n):
+    """The dW form of the large-model GEMM (gemm_tc.cu, TN mode): A = X^T and B = dY^T read MN-major straight from
+    batch-major [k = batch row][feature] tiles -- both operands in the SWIZZLE_128B_BASE32B layout (descriptor layout 1,
+    LBO = bytes between 32-wide feature blocks, SBO = 512, +1024 B per K = 8 step), instruction-descriptor bits 15 / 16
+    set; N = 256 spans two 128-column operand tiles laid out back to back (the stacked [Bh ; Bl] form)."""
+    rng = np.random.default_rng(11)
+    k = 32
+    X = trunc_tf32(rng.standard_normal((k, 128)).astype(np.float32))     # [k][m]
+    Y = trunc_tf32(rng.standard_normal((k, n)).astype(np.float32))       # [k][n]
+    mn = lambda lbo, sbo: ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1 << 46) | (1 << 61)
+    got = run(lib, base32_image(X), base32_image(Y), mn(k * 128, 512), mn(k * 128, 512), idesc(n, a_mn=True, b_mn=True),
+              k // 8, 1024, 1024, n)
+    ref = X.astype(np.float64).T @ Y.astype(np.float64)
+    assert relerr(got, ref) <= 2e-6

@@ -89,6 +89,7 @@ _PROTOTYPES = {
     "vae_pack_train": (C.c_int, [C.POINTER(VaePackPlan), C.c_int64, _P]),
     "vae_split_tf32": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "vae_transpose_split_tf32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "vae_gemm_tn_3xtf32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, _P]),
     "vae_gemm_nt_3xtf32": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_int64, _P,
                                      C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
     "vae_umma_probe": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32,

@@ -3,6 +3,9 @@
 // BASELINE.json configs[4] (D=1024, width 4096, batch 65 536).
 //
 //   C[M,N] = epi( A[M,K] * B[N,K]^T )        ("NT": both operands K-contiguous, row-major)
+//   C[M,N] = At[K,M]^T * Bt[K,N]              ("TN": both operands given K-row-major, i.e. M- / N-contiguous: the dW =
+//                                              X^T dY form, read straight from the batch-major activations / gradients
+//                                              through MN-major tcgen05 descriptors -- no transposed copies in HBM)
 //
 // Plain TF32 (10-bit mantissa) cannot meet the path's rel-1e-5-per-step tolerance, so every
 // FP32 operand X is split as X ~= hi + lo with hi = TF32(X) and lo = TF32(X - hi) (both rounded
@@ -90,9 +93,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile for kind::tf32 (TN mode): the tile is stored as 32-wide M (or N) blocks of [32 k-rows][128 B],
+// one TMA box {32 floats, 32 rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B each (32-byte chunk index XOR (row % 4)) --
+// the SWIZZLE_128B_BASE32B layout (type 1), the only one an MN-major TF32 operand is read correctly from
+// (tests/test_gpu_umma_probe.py).  LBO = 4096 B between the 32-wide blocks, SBO = 512 B between 4-row groups; a K = 8
+// step is 8 rows = 1024 B further.
+__device__ __forceinline__ uint64_t make_mnmajor_b32_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, N>>3 at [17,23), M>>4 at [24,29); bits 15 / 16: A / B is MN-major
+__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N, bool mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // The tensor core accumulates in FP32 with round-toward-zero: a long accumulation chain in
@@ -136,7 +147,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // correction accumulator all running ACROSS tiles: the TMA producer and the MMA issuer start tile
 // t+1 while the epilogue warps still drain / store tile t, so neither the pipeline fill nor the
 // epilogue is exposed per tile.  TMEM (512 columns): main0 | corr0 | main1 | corr1.
-template <int MC>
+template <int MC, bool TN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -209,6 +220,28 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           mbar_wait(&empty_bar[s], ph ^ 1u);                 // slot free (first pass: immediately)
           uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
+          if (TN) {
+            // TN: operand tiles are 4 blocks of [32 k-rows][32 M- or N-floats] (box x = column, y = k row); a CTA of a
+            // multicast pair fetches 2 of the 4 blocks of the shared operand
+            constexpr int kBlk = 32 * TC_BK * 4;                                  // 4 KB
+            for (int j = 0; j < 4; ++j) {
+              if (CX == 1) {
+                tma_load_2d(st + 0 * TC_TILE_BYTES + j * kBlk, &tmAh, &full_bar[s], m0 + 32 * j, kb * TC_BK);
+                tma_load_2d(st + 1 * TC_TILE_BYTES + j * kBlk, &tmAl, &full_bar[s], m0 + 32 * j, kb * TC_BK);
+              } else if ((j >> 1) == (int)cx) {
+                tma_load_2d_mc(st + 0 * TC_TILE_BYTES + j * kBlk, &tmAh, &full_bar[s], m0 + 32 * j, kb * TC_BK, a_mask);
+                tma_load_2d_mc(st + 1 * TC_TILE_BYTES + j * kBlk, &tmAl, &full_bar[s], m0 + 32 * j, kb * TC_BK, a_mask);
+              }
+              if (CY == 1) {
+                tma_load_2d(st + 2 * TC_TILE_BYTES + j * kBlk, &tmBh, &full_bar[s], n0 + 32 * j, kb * TC_BK);
+                tma_load_2d(st + 3 * TC_TILE_BYTES + j * kBlk, &tmBl, &full_bar[s], n0 + 32 * j, kb * TC_BK);
+              } else if ((j >> 1) == (int)cy) {
+                tma_load_2d_mc(st + 2 * TC_TILE_BYTES + j * kBlk, &tmBh, &full_bar[s], n0 + 32 * j, kb * TC_BK, b_mask);
+                tma_load_2d_mc(st + 3 * TC_TILE_BYTES + j * kBlk, &tmBl, &full_bar[s], n0 + 32 * j, kb * TC_BK, b_mask);
+              }
+            }
+            continue;
+          }
           if (CX == 1) {
             tma_load_2d(st + 0 * TC_TILE_BYTES, &tmAh, &full_bar[s], kb * TC_BK, m0);
             tma_load_2d(st + 1 * TC_TILE_BYTES, &tmAl, &full_bar[s], kb * TC_BK, m0);
@@ -233,7 +266,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN), idesc2 = make_tf32_idesc(TC_BM, 2 * TC_BN);
+      constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN, TN), idesc2 = make_tf32_idesc(TC_BM, 2 * TC_BN, TN);
       uint32_t it = 0, gc = 0;                               // k-blocks, accumulator chunks so far
       for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -248,12 +281,14 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-          const uint64_t dAh = make_kmajor_sw128_desc(base + 0 * TC_TILE_BYTES), dAl = make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
-          const uint64_t dBh = make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES);   // Bh, and Bl right behind it
+          const uint64_t dAh = TN ? make_mnmajor_b32_desc(base + 0 * TC_TILE_BYTES) : make_kmajor_sw128_desc(base + 0 * TC_TILE_BYTES);
+          const uint64_t dAl = TN ? make_mnmajor_b32_desc(base + 1 * TC_TILE_BYTES) : make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
+          const uint64_t dBh = TN ? make_mnmajor_b32_desc(base + 2 * TC_TILE_BYTES) : make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES);   // Bh, and Bl right behind it
           const uint32_t tmem_main = tmem_acc + buf * (2 * TC_BN);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // +32 bytes per K=8 step inside the 128-byte row
+            // per K = 8 step: +32 bytes inside the 128-byte row (K-major) / 8 rows = 1024 bytes further (MN-major)
+            const uint64_t adv = (uint64_t)((TN ? k * 1024 : k * 8 * 4) >> 4);
             // Ah * [Bh ; Bl]^T in ONE N = 256 MMA: columns 0-127 main term, 128-255 first correction
             // (Ah is read from shared memory once instead of twice)
             umma_tf32(tmem_main, dAh + adv, dBh + adv, idesc2, !(first && k == 0));
@@ -420,12 +455,27 @@ static int tc_cluster_cap() {
   return v >= 4 ? 4 : v >= 2 ? 2 : 1;
 }
 
-template <int MC>
+// TN operand: K rows x `cols` floats row-major (leading dimension ld): boxes of 32 k-rows x 32 floats, SWIZZLE_128B_ATOM_32B
+static int make_operand_map_tn(CUtensorMap* tm, const float* ptr, int K, int cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VAE_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)K};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)TC_BK};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (TN operand) failed (CUresult %d)", (int)r); return VAE_ERR_CUDA; }
+  return 0;
+}
+
+template <int MC, bool TN = false>
 static int launch_gemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
                        float* d_C, int M, int N, int K, int64_t ldc, const float* d_bias, const float* d_mask, int64_t ldm,
                        int flags, int tiles_n, int tiles_m, cudaStream_t stream) {
   constexpr int CX = MC == 4 ? 2 : 1, CY = MC >= 2 ? 2 : 1;
-  VAE_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  VAE_CUDA_OK(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel<MC, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   // cluster tiles: ctn along N, ctm along M (an odd last M tile of a pair is all out-of-bounds: zero-filled
   // loads, masked stores); the persistent grid is one cluster per MC SMs, or fewer if there are fewer tiles
   const int ctn = tiles_n / CX, ctm = (tiles_m + CY - 1) / CY;
@@ -445,7 +495,7 @@ static int launch_gemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUt
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = MC > 1 ? 1 : 0;
-  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_nt_3xtf32_kernel<MC>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
+  VAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_nt_3xtf32_kernel<MC, TN>, tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm,
                                  flags, ctn, n_ctiles));
   count_launch();
   return 0;
@@ -500,6 +550,28 @@ int vae_gemm_nt_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ah, const
   if (mc == 4) return vae::launch_gemm<4>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
   if (mc == 2) return vae::launch_gemm<2>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
   return vae::launch_gemm<1>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, d_bias, d_mask, ldm, flags, tiles_n, tiles_m, st);
+}
+
+int vae_gemm_tn_3xtf32(int32_t M, int32_t N, int32_t K, const float* d_Ath, const float* d_Atl, int64_t lda,
+                       const float* d_Bth, const float* d_Btl, int64_t ldb, float* d_C, int64_t ldc, void* stream) {
+  VAE_REQUIRE(M > 0 && N > 0 && K > 0 && d_Ath && d_Atl && d_Bth && d_Btl && d_C, "vae_gemm_tn_3xtf32: bad arguments");
+  VAE_REQUIRE(lda >= M && ldb >= N && ldc >= N, "vae_gemm_tn_3xtf32: leading dimensions too small");
+  VAE_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "vae_gemm_tn_3xtf32: lda / ldb must be multiples of 4 floats (TMA 16-byte strides)");
+  VAE_REQUIRE((((uintptr_t)d_Ath | (uintptr_t)d_Atl | (uintptr_t)d_Bth | (uintptr_t)d_Btl) & 15) == 0,
+              "vae_gemm_tn_3xtf32: operands must be 16-byte aligned");
+  CUtensorMap tAh, tAl, tBh, tBl;
+  int rc;
+  const int tiles_m = (M + vae::TC_BM - 1) / vae::TC_BM, tiles_n = (N + vae::TC_BN - 1) / vae::TC_BN;
+  const int cap = vae::tc_cluster_cap();
+  const int mc = (cap >= 4 && tiles_m >= 2 && tiles_n % 2 == 0) ? 4 : (cap >= 2 && tiles_m >= 2) ? 2 : 1;
+  if ((rc = vae::make_operand_map_tn(&tAh, d_Ath, K, M, lda))) return rc;
+  if ((rc = vae::make_operand_map_tn(&tAl, d_Atl, K, M, lda))) return rc;
+  if ((rc = vae::make_operand_map_tn(&tBh, d_Bth, K, N, ldb))) return rc;
+  if ((rc = vae::make_operand_map_tn(&tBl, d_Btl, K, N, ldb))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mc == 4) return vae::launch_gemm<4, true>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, nullptr, nullptr, 0, 0, tiles_n, tiles_m, st);
+  if (mc == 2) return vae::launch_gemm<2, true>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, nullptr, nullptr, 0, 0, tiles_n, tiles_m, st);
+  return vae::launch_gemm<1, true>(tAh, tAl, tBh, tBl, d_C, M, N, K, ldc, nullptr, nullptr, 0, 0, tiles_n, tiles_m, st);
 }
 
 }  // extern "C"

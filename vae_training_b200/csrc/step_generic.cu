@@ -289,10 +289,6 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
   }
 }
 __global__ void step_inc_kernel(int32_t* step) { step[0] += 1; }
-__global__ void fill_ones_row_kernel(float* __restrict__ hi, float* __restrict__ lo, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { hi[i] = 1.0f; lo[i] = 0.0f; }
-}
 
 // ------------------------------------------------------------------- workspace
 struct Workspace {
@@ -307,12 +303,14 @@ struct Workspace {
   float* part;     // 3 * kMaxPart
   float* colpart;  // kColParts * max_width (two-stage column sums)
   float* grad;     // n_params
-  // tensor-core route (use_tc): 3xTF32 operand staging, reused layer after layer
+  // tensor-core route (use_tc): 3xTF32 operand staging
   bool tc;
-  float *xh, *xl;       // split(layer input)            rows x maxw
-  float *xth, *xtl;     // transpose_split(layer input)  maxw x rows
-  float *dyh, *dyl;     // split(dY)                     rows x maxw
-  float *dyth, *dytl;   // transpose_split(dY)           maxw x rows
+  // split(layer input) of every encoder / decoder layer, rows x in_i: written by the forward pass (A operand of
+  // Y = X W^T), read again by the backward pass as the MN-major A operand of dW = X^T dY (vae_gemm_tn_3xtf32) -- the
+  // activations are split once per step and never transposed
+  float *enc_xh[VAE_MAX_HIDDEN + 1], *enc_xl[VAE_MAX_HIDDEN + 1];
+  float *dec_xh[VAE_MAX_HIDDEN + 1], *dec_xl[VAE_MAX_HIDDEN + 1];
+  float *dyh, *dyl;     // split(dY)  rows x maxw: A of dX = dY W^T and MN-major B of dW (reused layer after layer)
   float *wh, *wl;       // split(W) / transpose_split(W) maxw x maxw
   size_t bytes;
 };
@@ -348,9 +346,9 @@ static void carve(const VaeDesc* d, const Layout& L, int rows, void* base, Works
   w->tc = use_tc(L, rows);
   if (w->tc) {
     const size_t act = (size_t)rows * L.max_width, ww = (size_t)L.max_width * L.max_width;
-    w->xh = take(act); w->xl = take(act);
-    w->xth = take(act + rows); w->xtl = take(act + rows);      // + the all-ones row (bias gradient)
-    w->dyh = take(act); w->dyl = take(act); w->dyth = take(act); w->dytl = take(act);
+    for (int i = 0; i < L.n_enc; ++i) { w->enc_xh[i] = take((size_t)rows * L.enc_sizes[i]); w->enc_xl[i] = take((size_t)rows * L.enc_sizes[i]); }
+    for (int i = 0; i < L.n_dec; ++i) { w->dec_xh[i] = take((size_t)rows * L.dec_sizes[i]); w->dec_xl[i] = take((size_t)rows * L.dec_sizes[i]); }
+    w->dyh = take(act); w->dyl = take(act);
     w->wh = take(ww); w->wl = take(ww);
   }
   w->bytes = off;
@@ -366,18 +364,20 @@ static inline int ew_grid(int64_t total) {
 // Forward MLP: acts[i] = relu?(in_i W_i + b_i)   (networks.py:28-39)
 static int mlp_forward(cudaStream_t s, const float* params, const int* sizes, int n_layers,
                        const int64_t* w_off, const int64_t* b_off, const float* input, int rows,
-                       float* const* acts, const Workspace* tcw = nullptr) {
+                       float* const* acts, const Workspace* tcw = nullptr, float* const* xh = nullptr,
+                       float* const* xl = nullptr) {
+  // tcw + xh / xl: the tensor-core route; xh[i] / xl[i] receive the TF32 split of layer i's input (kept for backward)
   const float* h = input;
   for (int i = 0; i < n_layers; ++i) {
     const int in = sizes[i], out = sizes[i + 1];
     const int flags = GEMM_BIAS | (i + 1 < n_layers ? GEMM_RELU : 0);
     if (tcw && tcw->tc) {
       // Y = X W + b as C[rows,out] = X[rows,in] * (W^T)[out,in]^T on the tensor cores
-      int rc = vae_split_tf32(h, tcw->xh, tcw->xl, (int64_t)rows * in, s);
+      int rc = vae_split_tf32(h, xh[i], xl[i], (int64_t)rows * in, s);
       if (rc) return rc;
       rc = vae_transpose_split_tf32(params + w_off[i], out, tcw->wh, tcw->wl, in, in, out, s);
       if (rc) return rc;
-      rc = vae_gemm_nt_3xtf32(rows, out, in, tcw->xh, tcw->xl, in, tcw->wh, tcw->wl, in, acts[i], out,
+      rc = vae_gemm_nt_3xtf32(rows, out, in, xh[i], xl[i], in, tcw->wh, tcw->wl, in, acts[i], out,
                               params + b_off[i], nullptr, 0, 1 | (i + 1 < n_layers ? 2 : 0), s);
       if (rc) return rc;
       h = acts[i];
@@ -397,7 +397,7 @@ static int mlp_backward(cudaStream_t s, const float* params, float* grad, const 
                         const int64_t* w_off, const int64_t* b_off, const float* input,
                         float* const* acts, int rows, const float* dout, float* ga, float* gb,
                         float* d_in, bool need_dx, bool acc_dx, const Workspace* tcw = nullptr,
-                        void* const* ready = nullptr) {
+                        void* const* ready = nullptr, float* const* xh = nullptr, float* const* xl = nullptr) {
   // ready (may be null): one cudaEvent_t per layer, recorded on `s` once that layer's kernel + bias gradient is final
   // (ready[0] = the LAST layer, the first one the backward pass finishes)
   const float* d = dout;
@@ -406,22 +406,15 @@ static int mlp_backward(cudaStream_t s, const float* params, float* grad, const 
     const int in = sizes[i], out = sizes[i + 1];
     const float* h_in = i == 0 ? input : acts[i - 1];
     if (tcw && tcw->tc && !acc_dx) {
-      // dW[in,out] = (X^T)[in,rows] * (dY^T)[out,rows]^T ; dX[rows,in] = dY[rows,out] * W[in,out]^T
-      int rc = vae_transpose_split_tf32(h_in, in, tcw->xth, tcw->xtl, rows, rows, in, s);
+      // dW[in,out] = X[rows,in]^T dY[rows,out]: both operands are read MN-major straight from the batch-major splits
+      // (X was split by the forward pass, dY is split once here for dW and dX) ; dX[rows,in] = dY[rows,out] * W[in,out]^T
+      int rc = vae_split_tf32(d, tcw->dyh, tcw->dyl, (int64_t)rows * out, s);
       if (rc) return rc;
-      rc = vae_transpose_split_tf32(d, out, tcw->dyth, tcw->dytl, rows, rows, out, s);
+      rc = vae_gemm_tn_3xtf32(in, out, rows, xh[i], xl[i], in, tcw->dyh, tcw->dyl, out, grad + w_off[i], out, s);
       if (rc) return rc;
-      // [X^T ; 1] (in+1 rows): the extra all-ones row makes the same GEMM produce the bias
-      // gradient, which sits right behind the kernel in the flat layout
-      if (b_off[i] != w_off[i] + (int64_t)in * out) { set_error("flat layout: bias does not follow kernel"); return VAE_ERR_INVALID; }
-      fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, s>>>(tcw->xth + (size_t)in * rows, tcw->xtl + (size_t)in * rows, rows);
-      VAE_LAUNCH_OK("fill_ones_row_kernel");
-      rc = vae_gemm_nt_3xtf32(in + 1, out, rows, tcw->xth, tcw->xtl, rows, tcw->dyth, tcw->dytl, rows, grad + w_off[i], out,
-                              nullptr, nullptr, 0, 0, s);
+      rc = colsum(s, d, out, nullptr, 0, rows, out, grad + b_off[i], tcw->colpart);     // bias gradient
       if (rc) return rc;
       if (i > 0 || need_dx) {
-        rc = vae_split_tf32(d, tcw->dyh, tcw->dyl, (int64_t)rows * out, s);
-        if (rc) return rc;
         rc = vae_split_tf32(params + w_off[i], tcw->wh, tcw->wl, (int64_t)in * out, s);
         if (rc) return rc;
         float* dst = i > 0 ? ((d == ga) ? gb : ga) : d_in;
@@ -485,13 +478,13 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
 
   float* mu = w.enc_act[L.n_enc - 1];
   if (mode != MODE_SAMPLE) {
-    rc = mlp_forward(s, params, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, rows, w.enc_act, &w);
+    rc = mlp_forward(s, params, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, rows, w.enc_act, &w, w.enc_xh, w.enc_xl);
     if (rc) return rc;
   }
   const int g_lat = ew_grid((int64_t)rows * Ld);
   reparam_kernel<<<g_lat, 256, 0, s>>>(mu, d_z, ldz, lv, rows, Ld, mode == MODE_SAMPLE, w.zs, part_mu2);
   VAE_LAUNCH_OK("reparam_kernel");
-  rc = mlp_forward(s, params, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, rows, w.dec_act, &w);
+  rc = mlp_forward(s, params, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, rows, w.dec_act, &w, w.dec_xh, w.dec_xl);
   if (rc) return rc;
   float* sig_out = nullptr;
   if (desc->sig_decoder) {
@@ -517,7 +510,7 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   // (epsilon_p, epsilon), encoder layers last -> first.  Two-decoder (sigmoid) models report everything at the end.
   const bool seg_events = ready != nullptr && !desc->sig_decoder;
   rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.dec_w, L.dec_b, w.zs, w.dec_act, rows,
-                    w.dxhat, w.ga, w.gb, w.dzs, true, false, &w, seg_events ? ready : nullptr);
+                    w.dxhat, w.ga, w.gb, w.dzs, true, false, &w, seg_events ? ready : nullptr, w.dec_xh, w.dec_xl);
   if (rc) return rc;
   if (desc->sig_decoder) {
     rc = mlp_backward(s, params, grad, L.dec_sizes, L.n_dec, L.sig_w, L.sig_b, w.zs, w.sig_act, rows,
@@ -530,7 +523,7 @@ static int run(const VaeDesc* desc, const float* params, const float* d_x, const
   VAE_LAUNCH_OK("latent_grad_kernel");
   if (seg_events) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[L.n_dec], s));
   rc = mlp_backward(s, params, grad, L.enc_sizes, L.n_enc, L.enc_w, L.enc_b, d_x, w.enc_act, rows,
-                    w.dzs, w.ga, w.gb, nullptr, false, false, &w, seg_events ? ready + L.n_dec + 1 : nullptr);
+                    w.dzs, w.ga, w.gb, nullptr, false, false, &w, seg_events ? ready + L.n_dec + 1 : nullptr, w.enc_xh, w.enc_xl);
   if (rc) return rc;
   if (ready && !seg_events) VAE_CUDA_OK(cudaEventRecord((cudaEvent_t)ready[0], s));
   return 0;

@@ -323,6 +323,17 @@ def gemm_nt_3xtf32(Ah, Al, Bh, Bl, bias=None, relu=False, mask=None, out=None) -
     return C_
 
 
+def gemm_tn_3xtf32(Ath, Atl, Bth, Btl, out=None) -> torch.Tensor:
+    """C[M,N] = (Ath+Atl)[K,M]^T @ (Bth+Btl)[K,N] on the tensor cores (3xTF32, MN-major operands)."""
+    K, M = Ath.shape
+    N = Bth.shape[1]
+    C_ = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=Ath.device)
+    check(_lib.load().vae_gemm_tn_3xtf32(M, N, K, _ptr(Ath, torch.float32, "Ath"), _ptr(Atl, torch.float32, "Atl"), M,
+                                         _ptr(Bth, torch.float32, "Bth"), _ptr(Btl, torch.float32, "Btl"), N, _ptr(C_), N,
+                                         _stream()), "vae_gemm_tn_3xtf32")
+    return C_
+
+
 def ffma_probe(blocks: int, threads: int, iters: int, sink: torch.Tensor) -> float:
     flops = C.c_double(0.0)
     check(_lib.load().vae_ffma_probe(_ptr(sink, torch.float32, "sink"), blocks, threads, iters, C.byref(flops),
