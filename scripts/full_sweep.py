@@ -23,10 +23,14 @@ def main():
     ap.add_argument("--which", default="all")
     ap.add_argument("--num_batches", type=int, default=None)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--emulate", default=None, help="RANK/WORLD: run that rank's share of a WORLD-GPU sweep alone on this GPU")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    if world > 1:
+    emulate = args.emulate is not None
+    if emulate:
+        rank, world = (int(v) for v in args.emulate.split("/"))
+    if world > 1 and not emulate:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     runs = sweep.builtin_runs(args.which, args.num_batches)
@@ -48,7 +52,7 @@ def main():
             "final_encoder_logvar": [float(v) for v in m.var_enc[-1].cpu().numpy()],
             "final_decoder_logvar": float(m.var_dec[-1].cpu().numpy()[0]),
             "stats_last": {k: float(v[-1]) for k, v in m.stats.items()}})
-    if world > 1:
+    if world > 1 and not emulate:
         gathered = [None] * world
         dist.all_gather_object(gathered, summary)
         if rank == 0:

@@ -122,7 +122,7 @@ def run_sweep(all_args, rank=0, world=1, save=True, verbose=False, timings=None)
         models.append(runmod.get_model(a, ds, out_dir, verbose=verbose))
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    train_many(models, save=save)
+    train_many(models, save=save, timings=timings)
     torch.cuda.synchronize()
     if timings is not None:
         timings["setup_seconds"] = t1 - t0                    # datasets, initial parameters, uploads

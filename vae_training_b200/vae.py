@@ -290,7 +290,7 @@ class VAEModel:
         self.dataset.save(os.path.join(self.dirname, "dataset.pk"))
 
 
-def train_many(models: Sequence[VAEModel], save=True):
+def train_many(models: Sequence[VAEModel], save=True, timings: Optional[dict] = None):
     """Packed sweep: every model follows its own reference schedule, but all models whose
     shape has a fused kernel advance together, one persistent launch per chunk (one CTA per
     model).  Models stay step-aligned; a chunk ends at the nearest event of any model."""
@@ -300,12 +300,15 @@ def train_many(models: Sequence[VAEModel], save=True):
     # One pack per fused-kernel class (single-CTA models / cluster models).  The two packs are
     # independent serial chains, so they run CONCURRENTLY: one host thread + one CUDA stream per
     # class (the ctypes calls release the GIL; torch's current stream is thread-local).
-    def run_pack(fused, stream, errors):
+    def run_pack(fused, stream, errors, barrier):
+        import time
+        t_begin = time.perf_counter()
         try:
             with torch.cuda.stream(stream):
                 scratch = ops.fused_scratch(len(fused), fused[0].device)
                 b = 0
                 plan, plan_ids = None, None
+                first = True
                 while True:
                     active = [m for m in fused if b < m.num_batches]
                     if not active:
@@ -317,13 +320,26 @@ def train_many(models: Sequence[VAEModel], save=True):
                     ids = tuple(id(m) for m in active)
                     if ids != plan_ids:         # the pack only changes when a run finishes: re-prepare then
                         plan, plan_ids = ops.pack_prepare([m._job for m in active], scratch), ids
+                    if first:
+                        # CUDA loads kernels lazily, and loading one while ANOTHER stream's long persistent kernel is
+                        # running waits for that kernel to finish: the ~30 kernels of this pack's event path would each
+                        # stall behind a 0.8 s hidden-layer chunk of the other pack (measured: a 4-run single-Dense pack
+                        # took 29 s instead of 4.6 s beside one sphere chain).  So every pack runs its first events and
+                        # prepares its plan (which loads its fused kernel) before ANY pack starts a persistent launch.
+                        stream.synchronize()
+                        barrier.wait()
+                        first = False
                     ops.pack_train(plan, c)
                     for m in active:
                         m._loss_pieces.append(m._chunk_loss[:c].clone())
                         m.batchnum = nxt
                     b = nxt
                 stream.synchronize()
+            if timings is not None:
+                timings[f"class{fused[0].fused_class}_pack_seconds"] = time.perf_counter() - t_begin
+                timings[f"class{fused[0].fused_class}_pack_runs"] = len(fused)
         except BaseException as e:          # re-raised on the caller's thread
+            barrier.abort()
             errors.append(e)
 
     packs = [[m for m in models if m.fused_class == cls] for cls in (1, 2)]
@@ -333,9 +349,10 @@ def train_many(models: Sequence[VAEModel], save=True):
         dev = packs[0][0].device
         torch.cuda.current_stream(dev).synchronize()           # state uploads are complete
         errors, threads = [], []
+        barrier = threading.Barrier(len(packs))
         for p_ in packs:
             st = torch.cuda.Stream(device=dev)
-            th = threading.Thread(target=run_pack, args=(p_, st, errors))
+            th = threading.Thread(target=run_pack, args=(p_, st, errors, barrier))
             th.start()
             threads.append(th)
         for th in threads:
