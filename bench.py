@@ -371,19 +371,44 @@ def tf32_peak(ctx):
     return 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
+def ops_param_count(spec):
+    from vae_training_b200 import ops
+    return ops.param_count(spec.desc())
+
+
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling
+    recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)"
+    except (OSError, ValueError, KeyError):
+        return 6650.0, "6650 GB/s of fallback (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
 def pack_roofline(spec, n_models, K, ms_launch, peak, traffic_key, tensor_peak=None):
     flop_step = spec.flops_per_step()
     achieved = flop_step * n_models * K / (ms_launch * 1e-3) / 1e12            # per GPU, algorithmic flops only
     if tensor_peak is not None:       # the tcgen05 3xTF32 kernel (fused_mlp_tc.cu)
-        return {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+        # A GPU-filling pack of hidden-layer models does not fit the 126 MB L2 (4.5 MB of state + exchange per model):
+        # ncu shows 9 MB of DRAM traffic per model-step and long-scoreboard (global load) as the top stall, with the tensor
+        # pipe 11 % active -- the bound that matters is HBM.  Algorithmic bytes per model-step (SURVEY.md 8d): parameters
+        # and both Adam moments read and written once = 24 B per parameter.
+        n_par = int(ops_param_count(spec))
+        alg_bytes = 24.0 * n_par
+        hbm_peak, peak_src = hbm_peak_gbs()
+        gbs = alg_bytes * n_models * K / (ms_launch * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "traffic": traffic_of(traffic_key),
                 "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
-                                f"'{traffic_key}' in profiles/traffic.json (null = not captured for this exact command)",
-                "note": f"achieved = {flop_step} algorithmic GEMM flops/model-step x model-steps/s on one GPU over the median "
-                        f"launch; peak = cuBLAS TF32 GEMM measured in this run ({tensor_peak:.0f} TFLOP/s; MEASURED_PEAKS.json "
-                        "holds only bf16).  FP32-level accuracy costs three TF32 MMAs per product (frac <= 1/3 by construction) "
-                        "and the step is a serial chain of 23 small GEMMs per model on ONE SM each (M = 128 batch tile, N <= 208, "
-                        "K <= 200): the kernel is shared-memory-bandwidth / store-bandwidth bound, see DESIGN.md 4.2b"}
+                                f"'{traffic_key}' in profiles/traffic.json (null = not captured for this exact command); "
+                                f"algorithmic bytes of the same launch: {alg_bytes * n_models * K:.0f}",
+                "tensor": {"achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                           "note": "algorithmic GEMM flops over the cuBLAS TF32 GEMM rate measured in this run; FP32-level "
+                                   "accuracy costs three TF32 MMAs per product (frac <= 1/3 by construction)"},
+                "note": f"achieved = {alg_bytes:.0f} algorithmic bytes/model-step (p, m, v of {n_par} parameters read + written) "
+                        f"x model-steps/s on one GPU over the median launch; peak = {peak_src}; ncu: tensor pipe 11 % active, "
+                        "L2 hit rate 42 %, top stall long-scoreboard (profiles/r02_fused_mlp_tc_ncu_full.txt, DESIGN.md 4.2b)"}
     return {"bound": "fp32-alu (on-chip persistent kernel: neither hbm nor tensor bound; SURVEY.md 8d)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic_of(traffic_key),
@@ -426,7 +451,7 @@ def measure_pack(ctx, workload, n_models, K, W, peak, first_index=0, want_states
            "launch_plan": {"class": runs.plan.cls, "models_per_cta": runs.plan.gm, "cluster": runs.plan.cluster,
                            "tensor_core_kernel": bool(runs.plan.tc)},
            "gpu_launches": int(launches),
-           "kernel": ("fused_mlp_tc_kernel (tcgen05 3xTF32, one CTA per model)" if tensor_peak is not None else
+           "kernel": (f"fused_mlp_tc_kernel (tcgen05 3xTF32, {runs.plan.cluster} CTA(s) per model)" if tensor_peak is not None else
                       "fused_mlp_kernel (FP32 FFMA, one cluster per model)" if runs.plan.cls == 2 else "fused_small_kernel"),
            "roofline": pack_roofline(specs[0], n_models, K, ms, peak, f"{workload}_m{n_models}_k{K}", tensor_peak)}
     if want_states:
