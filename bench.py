@@ -763,7 +763,9 @@ def run_b200(args):
                             "(vae_pack_train) -> D2H copy of state + per-step losses]; rounds are pipelined (the H2D engine, "
                             "the D2H engine and the SMs work on different sub-packs), the streams are joined at the end of "
                             "the R-round window, value = models x K x R / window (median of 5 windows, max over ranks); the "
-                            "pattern is one CUDA graph; `joined_every_round` = the same call joined on the launching stream "
+                            "pattern is one CUDA graph (back-to-back rounds on four streams also hide the gap between consecutive "
+                            "launches of one stream, which `value` -- the median single launch -- includes: at long launches "
+                            "e2e can come out a few percent above it); `joined_every_round` = the same call joined on the launching stream "
                             "after every round (train_host_all); first-round losses checked bit-identical to the "
                             "single-launch pack"},
             "eps_sharing_ab": {"unit": UNIT, **ab,
