@@ -811,6 +811,35 @@ def test_fused_tc_cluster_sizes_are_bit_identical(ops, lib, monkeypatch, cs):
     assert ops.pack_prepare([job], ops.fused_scratch(1)).cluster == 8        # a lone chain gets the largest cluster
 
 
+def test_fused_tc_cluster_stress_is_bit_identical(monkeypatch):
+    """Race stress of the cluster mode: 18 models x 8 CTAs (144 co-resident CTAs, every exchange through L2 + cluster
+    barriers) for 600 steps in two launches reproduce the one-CTA-per-model run bit for bit -- whole device arena
+    (parameters, moments, keys, step counters, losses).  scratch/tc_cluster_stress.py is the long form (2000 steps,
+    every cluster size, two shapes)."""
+    import bench
+    from vae_training_b200 import init
+    from vae_training_b200.packed import PackedRuns
+    monkeypatch.setenv("VAE_MLP_TC", "1")
+    n, nm = 600, 18
+    specs = bench.make_specs("sphere_dd5_pd16_ld16", nm)
+    states = [init.initial_state(s) for s in specs]
+
+    def run(cs):
+        monkeypatch.setenv("VAE_MLP_TC_CLUSTER", cs)
+        runs = PackedRuns(specs, max_chunk=n)
+        runs.upload(states)
+        runs.prepare()
+        assert runs.plan.tc == 1 and runs.plan.cluster == int(cs)
+        for chunk in (250, 350):
+            runs.train_steps(chunk)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(runs.loss).all())
+        return runs.arena.view(torch.int32).clone()
+    ref = run("1")
+    for cs in ("8", "4"):
+        assert torch.equal(ref, run(cs)), cs
+
+
 def test_fused_tc_nonzero_moments_on_padding_rows(ops, lib, monkeypatch):
     monkeypatch.setenv("VAE_MLP_TC", "1")
     monkeypatch.setenv("VAE_MLP_TC_CLUSTER", "4")
