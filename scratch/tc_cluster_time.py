@@ -19,7 +19,7 @@ models = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 
 for wl in ("sphere_dd3_pd3_ld6", "sphere_dd5_pd16_ld16"):
     for nm in models:
         run(wl, nm, 200, "0", None)
-        for cs in ("1", "2", "4", "8"):
+        for cs in ("4", "8", "16"):
             try:
                 run(wl, nm, 200, "1", cs)
             except Exception as e:

@@ -64,7 +64,8 @@ constexpr int kTMaxN = 208;                     // most B rows (accumulator colu
 constexpr int kTRingBytes = 176 * 1024;         // the operand ring; a GEMM cuts it into stages of its own size
 constexpr int kTSmemBytes = kTRingBytes + 1024;
 constexpr int kTMaxL = VAE_MAX_HIDDEN + 1;
-constexpr int kTMaxCluster = 8;                 // CTAs per model in the latency configuration (portable cluster size)
+constexpr int kTMaxCluster = 16;                // most CTAs per model (16 = non-portable cluster size, forced by VAE_MLP_TC_CLUSTER=16 only)
+constexpr int kTAutoCluster = 8;                // largest cluster the library picks on its own (portable)
 constexpr int kTNarrowGroups = 8;               // layers of at most this many 8-column groups are not cut (CTA 0 owns them)
 // tensor maps of a model: per layer [W^T, W (group-major), input batch-major, input feature-major, dY feature-major],
 // then the three batch-major gradient buffers
@@ -1081,9 +1082,10 @@ int mlp_tc_prepare(int n_jobs, int* cluster) {
   const char* e = getenv("VAE_MLP_TC_CLUSTER");
   if (e && e[0]) {
     const int v = atoi(e);
-    cs = v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
+    cs = v >= 16 ? 16 : v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
+    if (cs == 16) VAE_CUDA_OK(cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   } else {
-    for (int c = kTMaxCluster; c > 1; c >>= 1) {
+    for (int c = kTAutoCluster; c > 1; c >>= 1) {
       int fit = 0;
       if (tc_active_clusters(c, &fit) != 0) { cudaGetLastError(); continue; }
       if (n_jobs <= fit) { cs = c; break; }
