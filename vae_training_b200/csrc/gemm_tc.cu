@@ -78,6 +78,15 @@ __device__ __forceinline__ void tc_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// One lane of the converged warp (1 in the elected lane).  The producer and MMA warps run their loops with all 32 lanes
+// on warp-uniform values and predicate only the TMA / MMA / commit instructions on it: inside `if (lane == 0)` the
+// compiler must assume divergent operands and wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST waterfall
+// (~70 - 100 cycles per instruction; measured on fused_mlp_tc.cu).
+__device__ __forceinline__ uint32_t tc_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -208,8 +217,8 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const uint32_t tmem_acc = tmem_base_s;
 
   if (warp == 0) {
-    // ===================== TMA producer
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues)
+    {
       uint32_t it = 0;                                       // k-blocks issued so far, across tiles
       for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
         int m0, n0;
@@ -219,6 +228,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           const uint32_t ph = (it / TC_STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);                 // slot free (first pass: immediately)
           uint8_t* st = smem + (size_t)s * TC_STAGE_BYTES;
+          if (!tc_elect()) { __syncwarp(); continue; }
           mbar_expect_tx(&full_bar[s], TC_STAGE_BYTES);
           if (TN) {
             // TN: operand tiles are 4 blocks of [32 k-rows][32 M- or N-floats] (box x = column, y = k row); a CTA of a
@@ -240,6 +250,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 tma_load_2d_mc(st + 3 * TC_TILE_BYTES + j * kBlk, &tmBl, &full_bar[s], n0 + 32 * j, kb * TC_BK, b_mask);
               }
             }
+            __syncwarp();
             continue;
           }
           if (CX == 1) {
@@ -260,12 +271,13 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
             tma_load_2d_mc(st + 2 * TC_TILE_BYTES + off, &tmBh, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
             tma_load_2d_mc(st + 3 * TC_TILE_BYTES + off, &tmBl, &full_bar[s], kb * TC_BK, n0 + (int)cy * half_rows, b_mask);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp on uniform values, one elected lane issues)
+    {
       constexpr uint32_t idesc = make_tf32_idesc(TC_BM, TC_BN, TN), idesc2 = make_tf32_idesc(TC_BM, 2 * TC_BN, TN);
       uint32_t it = 0, gc = 0;                               // k-blocks, accumulator chunks so far
       for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
@@ -285,6 +297,7 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           const uint64_t dAl = TN ? make_mnmajor_b32_desc(base + 1 * TC_TILE_BYTES) : make_kmajor_sw128_desc(base + 1 * TC_TILE_BYTES);
           const uint64_t dBh = TN ? make_mnmajor_b32_desc(base + 2 * TC_TILE_BYTES) : make_kmajor_sw128_desc(base + 2 * TC_TILE_BYTES);   // Bh, and Bl right behind it
           const uint32_t tmem_main = tmem_acc + buf * (2 * TC_BN);
+          if (tc_elect()) {
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             // per K = 8 step: +32 bytes inside the 128-byte row (K-major) / 8 rows = 1024 bytes further (MN-major)
@@ -296,7 +309,10 @@ gemm_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
           }
           if (MC == 1) umma_commit(&empty_bar[s]);           // smem slot reusable once these MMAs retire
           else umma_commit_mc(&empty_bar[s], peers_mask);
-          if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) { umma_commit(&mfull_bar[buf]); ++gc; }
+          if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) umma_commit(&mfull_bar[buf]);
+          }
+          __syncwarp();
+          if ((kb % TC_CHUNK) == TC_CHUNK - 1 || kb == nkb - 1) ++gc;
         }
       }
     }
