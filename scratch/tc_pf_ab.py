@@ -5,7 +5,7 @@ from vae_training_b200 import init
 from vae_training_b200.packed import PackedRuns
 os.environ["VAE_MLP_TC"] = "1"
 for wl in ("sphere_dd3_pd3_ld6", "sphere_dd5_pd16_ld16"):
-    for nm, cs in ((148, "1"), (74, "2"), (33, "4"), (1, "1")):
+    for nm, cs in ((148, "1"), (296, "1"), (148, "2"), (74, "2"), (66, "4"), (33, "4"), (1, "1"), (1, "8")):
         os.environ["VAE_MLP_TC_CLUSTER"] = cs
         specs = bench.make_specs(wl, nm)
         runs = PackedRuns(specs, max_chunk=100)
