@@ -19,7 +19,7 @@ for line in out.splitlines():
         kern = m.group(1)
         hist[kern] = collections.Counter()
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
     if m and kern:
         op, mods = m.group(1), m.group(2)
         total[kern] += 1
