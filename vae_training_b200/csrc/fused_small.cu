@@ -242,8 +242,18 @@ __device__ __noinline__ void small_draw(float* zdst, float* gdst, const uint32_t
 // the eps-sharing group (plain shared-memory stores, CTA barriers only) -- used without clusters.
 // BT > 0 fixes the batch size at compile time (the grouped kernels are built for the reference's
 // batch of 100, run.py:14): the whole shared-memory layout becomes immediate offsets.
+#ifdef VAE_SMALL_TIMING
+__device__ unsigned long long g_small_t[8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SMALL_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_small_t[i] = gtimer(); } while (0)
+extern "C" int vae_small_timing(unsigned long long* out8) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(out8, g_small_t, 64); }
+#else
+#define SMALL_STAMP(i) do {} while (0)
+#endif
+
 template <class C, int GM, int BT>
 __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float* sm_cta) {
+  SMALL_STAMP(0);
   constexpr int D = C::D, L = C::L, DR = C::DR, DD = C::DD, G = C::G, LP = C::LP, DP = C::DP;
   constexpr int TI = C::TI, TJ = C::TJ, KS = C::KS;
   constexpr int LD = L + D;
@@ -261,8 +271,10 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   uint32_t* keys = reinterpret_cast<uint32_t*>(sm + y.keys);
 
   // ---- load state
+  SMALL_STAMP(1);
   for (int i = t; i < y.total; i += kT) sm[i] = 0.f;
   __syncthreads();
+  SMALL_STAMP(2);
   const int nflat = C::NFLAT + (tunable ? 1 : 0);
   for (int g = t; g < nflat; g += kT) {
     const int o = C::padded_of(g, tunable);
@@ -338,6 +350,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   const int gsize = __popc(gmask), gidx = __popc(gmask & ((1u << self) - 1u));
   const int draw_mode = gsize == 1 ? 0 : GM > 1 ? 2 : 1;
   __syncthreads();
+  SMALL_STAMP(3);
 
   const float invB = 1.0f / (float)B;
   const int npair_e = (((B * LD + 1) >> 1) + 1) >> 1;     // eps block pairs per step
@@ -629,6 +642,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     if (pipe) { cl_wait(); __syncthreads(); }     // eps_{s+1} complete everywhere; phase C done in this CTA
   }
   __syncthreads();
+  SMALL_STAMP(4);
   // ---- store state
   for (int g = t; g < nflat; g += kT) {
     const int o = C::padded_of(g, tunable);
@@ -639,6 +653,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     uint32_t* dst = t < 2 ? job.model_key : job.dataset_key;
     if ((t & 1) == 0) { dst[0] = ck0; dst[1] = ck1; }
   }
+  SMALL_STAMP(5);
 }
 
 // (id, D, L, DR, SIG, KIND, G, TI, TJ): every single-Dense shape of the two sweeps, plus one
