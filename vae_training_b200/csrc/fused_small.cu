@@ -380,13 +380,23 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     // ================= phase A: random draws (private mode: in step; cluster mode: one step ahead)
     if (!pipe) { draw_step(s); __syncthreads(); }
     // ================= phase B: one thread per batch row
+    // With 100 rows for 128 threads the fourth warp of a model has 4 busy lanes.  In the grouped kernel (4 models per
+    // CTA, B = 100) model 0's fourth warp takes the 4 leftover rows of ALL four models (lane -> model lane / 4, row
+    // 96 + lane % 4) and the other models' fourth warps skip phase B: one nearly empty warp pass instead of four.
+    // The arithmetic per row and the order of every sum are unchanged (see the reduction below).
+    constexpr bool kPackTail = GM == 4 && BT == 100;
+    const bool tail_warp = kPackTail && t >= 96;
+    const int mb = tail_warp ? ((t - 96) >> 2) & 3 : mi;                       // the model whose row this thread works on
+    float* smB = tail_warp ? sm_cta + mb * y.total : sm;
+    const float* Pb = smB + y.P;
+    const int b_first = !tail_warp ? t : (mi == 0 && t < 112) ? 96 + ((t - 96) & 3) : B;
     float kl_acc = 0.f, r2_acc = 0.f, rz_acc = 0.f;
     {
-      const float sd = sm[y.scal + 8 * slot + 1], inv_var = sm[y.scal + 8 * slot + 2];
+      const float sd = smB[y.scal + 8 * slot + 1], inv_var = smB[y.scal + 8 * slot + 2];
       const float gscale = inv_var * invB;
-      for (int b = t; b < B; b += kT) {
-        const float* zr = sm + y.z + zb * zstride + b * C::SZ;
-        const float* gr = sm + y.gn + zb * gstride + b * C::SG;
+      for (int b = b_first; b < B; b += kT) {
+        const float* zr = smB + y.z + zb * zstride + b * C::SZ;
+        const float* gr = smB + y.gn + zb * gstride + b * C::SG;
         // ---- generator transform (bit-exact with oracle/datasets.py)
         float x[DR];
         if constexpr (C::KIND == VAE_DATA_SPHERE) {
@@ -397,7 +407,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
 #pragma unroll
           for (int j = 0; j < DD; ++j) x[j] = __fdiv_rn(x[j], rad);
         } else if constexpr (C::KIND == VAE_DATA_LINEAR_GAUSSIAN) {
-          const float* A = sm + y.A;
+          const float* A = smB + y.A;
 #pragma unroll
           for (int i = 0; i < DD; ++i) {
             float acc = __fmul_rn(A[i * G], gr[0]);
@@ -406,27 +416,27 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
             x[i] = acc;
           }
         } else {
-          const float* A = sm + y.A;
+          const float* A = smB + y.A;
           float acc = 0.f;
 #pragma unroll
           for (int j = 0; j < DD; ++j) { x[j] = gr[j]; const float pr = __fmul_rn(x[j], A[j]); acc = j == 0 ? pr : __fadd_rn(acc, pr); }
           x[DD] = det_sigmoid(acc);
         }
-        float* hxc = sm + y.hx + b;
+        float* hxc = smB + y.hx + b;
 #pragma unroll
         for (int d = 0; d < DR; ++d) hxc[d * BP] = x[d];
         // ---- encoder: mu = x We + be   (only the DR non-padding columns contribute)
         float mu[LP];
 #pragma unroll
         for (int q = 0; q < LP / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(P + C::oBe + 4 * q);
+          const float4 v = *reinterpret_cast<const float4*>(Pb + C::oBe + 4 * q);
           mu[4 * q] = v.x; mu[4 * q + 1] = v.y; mu[4 * q + 2] = v.z; mu[4 * q + 3] = v.w;
         }
 #pragma unroll
         for (int d = 0; d < DR; ++d) {
 #pragma unroll
           for (int q = 0; q < LP / 4; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(P + C::oWe + d * LP + 4 * q);
+            const float4 w = *reinterpret_cast<const float4*>(Pb + C::oWe + d * LP + 4 * q);
             mu[4 * q] = fmaf(x[d], w.x, mu[4 * q]); mu[4 * q + 1] = fmaf(x[d], w.y, mu[4 * q + 1]);
             mu[4 * q + 2] = fmaf(x[d], w.z, mu[4 * q + 2]); mu[4 * q + 3] = fmaf(x[d], w.w, mu[4 * q + 3]);
           }
@@ -435,34 +445,34 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
         float dec[DP], sp[C::SIG ? DP : 1];
 #pragma unroll
         for (int q = 0; q < DP / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(P + C::oBd + 4 * q);
+          const float4 v = *reinterpret_cast<const float4*>(Pb + C::oBd + 4 * q);
           dec[4 * q] = v.x; dec[4 * q + 1] = v.y; dec[4 * q + 2] = v.z; dec[4 * q + 3] = v.w;
           if constexpr (C::SIG) {
-            const float4 u = *reinterpret_cast<const float4*>(P + C::oBs + 4 * q);
+            const float4 u = *reinterpret_cast<const float4*>(Pb + C::oBs + 4 * q);
             sp[4 * q] = u.x; sp[4 * q + 1] = u.y; sp[4 * q + 2] = u.z; sp[4 * q + 3] = u.w;
           }
         }
-        float* hzc = sm + y.hz + b;
+        float* hzc = smB + y.hz + b;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           kl_acc = fmaf(mu[l], mu[l], kl_acc);
-          const float zsl = fmaf(sm[y.sl + l], zr[l], mu[l]);
+          const float zsl = fmaf(smB[y.sl + l], zr[l], mu[l]);
           hzc[l * BP] = zsl;
 #pragma unroll
           for (int q = 0; q < DP / 4; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(P + C::oWd + l * DP + 4 * q);
+            const float4 w = *reinterpret_cast<const float4*>(Pb + C::oWd + l * DP + 4 * q);
             dec[4 * q] = fmaf(zsl, w.x, dec[4 * q]); dec[4 * q + 1] = fmaf(zsl, w.y, dec[4 * q + 1]);
             dec[4 * q + 2] = fmaf(zsl, w.z, dec[4 * q + 2]); dec[4 * q + 3] = fmaf(zsl, w.w, dec[4 * q + 3]);
             if constexpr (C::SIG) {
-              const float4 u = *reinterpret_cast<const float4*>(P + C::oWs + l * DP + 4 * q);
+              const float4 u = *reinterpret_cast<const float4*>(Pb + C::oWs + l * DP + 4 * q);
               sp[4 * q] = fmaf(zsl, u.x, sp[4 * q]); sp[4 * q + 1] = fmaf(zsl, u.y, sp[4 * q + 1]);
               sp[4 * q + 2] = fmaf(zsl, u.z, sp[4 * q + 2]); sp[4 * q + 3] = fmaf(zsl, u.w, sp[4 * q + 3]);
             }
           }
         }
         // ---- output, residual, d x_hat  (dec[] becomes d x_hat, sp[] becomes d sig_pre)
-        float* dxc = sm + y.dx + b;
-        float* dpc = sm + y.dp + b;
+        float* dxc = smB + y.dx + b;
+        float* dpc = smB + y.dp + b;
 #pragma unroll
         for (int d = 0; d < DP; ++d) {
           if (d < D) {
@@ -483,18 +493,18 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
           }
         }
         // ---- dzs = dxhat Wd^T (+ dpre Ws^T); dmu = dzs + mu/B; q = dzs * z1
-        float* dmc = sm + y.dm + b;
-        float* qc = sm + y.q + b;
+        float* dmc = smB + y.dm + b;
+        float* qc = smB + y.q + b;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int q = 0; q < DP / 4; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(P + C::oWd + l * DP + 4 * q);
+            const float4 w = *reinterpret_cast<const float4*>(Pb + C::oWd + l * DP + 4 * q);
             a0 = fmaf(dec[4 * q], w.x, a0); a1 = fmaf(dec[4 * q + 1], w.y, a1);
             a0 = fmaf(dec[4 * q + 2], w.z, a0); a1 = fmaf(dec[4 * q + 3], w.w, a1);
             if constexpr (C::SIG) {
-              const float4 u = *reinterpret_cast<const float4*>(P + C::oWs + l * DP + 4 * q);
+              const float4 u = *reinterpret_cast<const float4*>(Pb + C::oWs + l * DP + 4 * q);
               a0 = fmaf(sp[4 * q], u.x, a0); a1 = fmaf(sp[4 * q + 1], u.y, a1);
               a0 = fmaf(sp[4 * q + 2], u.z, a0); a1 = fmaf(sp[4 * q + 3], u.w, a1);
             }
@@ -504,9 +514,19 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
           qc[l * BP] = dz * zr[l];
         }
       }
-      kl_acc = warp_sum(kl_acc); r2_acc = warp_sum(r2_acc); rz_acc = warp_sum(rz_acc);
-      if ((t & 31) == 0) {
-        sm[y.red + 0 + (t >> 5)] = kl_acc; sm[y.red + 4 + (t >> 5)] = r2_acc; sm[y.red + 8 + (t >> 5)] = rz_acc;
+      if (tail_warp) {
+        // four lanes per model: the same pairing as the last two levels of warp_sum ((l0 + l2) + (l1 + l3)); a full
+        // warp_sum over this warp would only have added exact zeros before them
+        if (mi == 0) {
+          kl_acc += __shfl_xor_sync(0xffffffffu, kl_acc, 2); r2_acc += __shfl_xor_sync(0xffffffffu, r2_acc, 2); rz_acc += __shfl_xor_sync(0xffffffffu, rz_acc, 2);
+          kl_acc += __shfl_xor_sync(0xffffffffu, kl_acc, 1); r2_acc += __shfl_xor_sync(0xffffffffu, r2_acc, 1); rz_acc += __shfl_xor_sync(0xffffffffu, rz_acc, 1);
+          if (t < 112 && (t & 3) == 0) { smB[y.red + 0 + 3] = kl_acc; smB[y.red + 4 + 3] = r2_acc; smB[y.red + 8 + 3] = rz_acc; }
+        }
+      } else {
+        kl_acc = warp_sum(kl_acc); r2_acc = warp_sum(r2_acc); rz_acc = warp_sum(rz_acc);
+        if ((t & 31) == 0) {
+          sm[y.red + 0 + (t >> 5)] = kl_acc; sm[y.red + 4 + (t >> 5)] = r2_acc; sm[y.red + 8 + (t >> 5)] = rz_acc;
+        }
       }
     }
     if (pipe) {                     // next step's draws; then "my share of eps_{s+1} is stored everywhere"
