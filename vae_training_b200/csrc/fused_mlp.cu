@@ -57,6 +57,10 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// idx / d for 0 <= idx < 2^22 and quotients < 2^12 through one float multiply: (idx + 0.5) / d is at least 0.5 / d away from
+// an integer, far more than the 2^-23 relative error of the two roundings, so truncation gives the exact quotient.
+__device__ __forceinline__ int fast_div(int idx, float inv_d) { return __float2int_rz(((float)idx + 0.5f) * inv_d); }
+
 struct Slice { int c0, w; };
 __device__ __forceinline__ Slice slice_of(int n, int rank, int cs) {
   const int chunk = (n + cs - 1) / cs;
@@ -79,6 +83,41 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Bulk (TMA) copies for whole activation arrays: ONE instruction of one thread moves K x BP floats from the L2-resident
+// workspace into shared memory (the LDGSTS form costs K * BP / 128 warp instructions at 8 cycles each: ~1.3 k cycles of
+// issue per 80 KB operand); completion is counted in bytes on an mbarrier every thread waits on.
+__device__ __forceinline__ uint32_t m_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void m_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m_smem(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void m_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m_smem(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void m_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = m_smem(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// dst (smem, [nrows][BP]) <- src (global, same layout); call from ONE thread, after m_expect_tx of the total
+__device__ __forceinline__ void bulk_rows(float* dst, const float* src, int nrows, int BP, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)(nrows * BP) * 4u;
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(m_smem(dst) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(m_smem(bar)) : "memory");
+  }
+}
+// This thread's global stores become visible to the async proxy (the peers' bulk copies after the next cluster barrier).
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // dst (smem, [nrows][BP]) <- src (global, same layout), asynchronous: cp_async_wait_all() +
 // __syncthreads() before use
 __device__ __forceinline__ void load_rows(float* dst, const float* src, int nrows, int BP) {
@@ -90,79 +129,98 @@ __device__ __forceinline__ void load_rows(float* dst, const float* src, int nrow
 //   Ws (smem, [K][W4]) must already be staged; AT smem [K][BP].
 //   relu: max(.,0).  maskT != nullptr: multiply by (maskT[(o0+j)][b] > 0) (relu backward).
 //   Rows b >= B are written as 0.
+struct GemmArgs {
+  const float* AT; int K; const float* Ws; int W4, w; const float* add_g; int o0; bool relu;
+  const float* maskT; float* outT_g; int BP, B;
+};
+// One task of tile_gemm: tt = 2 * tile + (half of the k range).  All 32 lanes of a warp call it together
+// (the two lanes of a pair exchange their partial sums with a shuffle).
+__device__ __forceinline__ void gemm_task(const GemmArgs& g, int tt, int ntile, int NG) {
+  const int K = g.K, W4 = g.W4, BP = g.BP;
+  const int kh = (K + 1) >> 1;
+  const bool live = tt < 2 * ntile;
+  const int tile = live ? tt >> 1 : ntile - 1, half = tt & 1;
+  const int cg = tile / NG, rg = tile - cg * NG;
+  // Blackwell packed FP32 FMA (FFMA2): accumulators are row pairs, (a.x, a.y) / (a.z, a.w) are natural
+  // register pairs of the 128-bit load; only the weight has to be duplicated into a pair.  Every lane
+  // of a pair performs the same RN fma as the scalar form: results are unchanged.
+  float2 acc2[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { acc2[j][0] = make_float2(0.f, 0.f); acc2[j][1] = make_float2(0.f, 0.f); }
+  const float* ap = g.AT + 4 * rg;
+  const float* wp = g.Ws + 4 * cg;
+  const int kbeg = half ? kh : 0, kend = half ? K : kh;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};          // loaded up front: the L2 round trip overlaps the k loop
+  if (g.add_g && live && !half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (4 * cg + j < g.w) bias[j] = g.add_g[g.o0 + 4 * cg + j];
+  }
+#pragma unroll 4
+  for (int k = kbeg; k < kend; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(ap + k * BP);
+    const float4 wv = *reinterpret_cast<const float4*>(wp + k * W4);
+    const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
+    const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 ww = make_float2(wj[j], wj[j]);
+      acc2[j][0] = __ffma2_rn(ww, a01, acc2[j][0]);
+      acc2[j][1] = __ffma2_rn(ww, a23, acc2[j][1]);
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { acc[j][0] = acc2[j][0].x; acc[j][1] = acc2[j][0].y; acc[j][2] = acc2[j][1].x; acc[j][3] = acc2[j][1].y; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[j][r] += __shfl_xor_sync(0xffffffffu, acc[j][r], 1);
+  if (!live || half) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = 4 * cg + j;
+    if (col >= g.w) continue;
+    float o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float v = acc[j][r] + bias[j];
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.maskT) v = g.maskT[(g.o0 + col) * BP + 4 * rg + r] > 0.f ? v : 0.f;
+      if (4 * rg + r >= g.B) v = 0.f;
+      o[r] = v;
+    }
+    *reinterpret_cast<float4*>(g.outT_g + (size_t)(g.o0 + col) * BP + 4 * rg) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ AT, int K, const float* __restrict__ Ws, int W4,
                                           int w, const float* __restrict__ add_g, int o0, bool relu,
                                           const float* __restrict__ maskT, float* __restrict__ outT_g, int BP, int B) {
   // 4x4 output tiles; the reduction over k is split between the two lanes of a pair (halves
   // of K), combined with a shuffle: twice the warps in flight for the same instruction count.
+  const GemmArgs g{AT, K, Ws, W4, w, add_g, o0, relu, maskT, outT_g, BP, B};
   const int ncg = W4 >> 2, NG = BP >> 2, ntile = ncg * NG;
-  const int kh = (K + 1) >> 1;
   for (int tt0 = 0; tt0 < 2 * ntile; tt0 += kMT) {
-    const int tt = tt0 + (int)threadIdx.x;
     if (tt0 + ((int)threadIdx.x & ~31) >= 2 * ntile) break;              // warp-uniform
-    const bool live = tt < 2 * ntile;
-    const int tile = live ? tt >> 1 : ntile - 1, half = tt & 1;
-    const int cg = tile / NG, rg = tile - cg * NG;
-    // Blackwell packed FP32 FMA (FFMA2): accumulators are row pairs, (a.x, a.y) / (a.z, a.w) are natural
-    // register pairs of the 128-bit load; only the weight has to be duplicated into a pair.  Every lane
-    // of a pair performs the same RN fma as the scalar form: results are unchanged.
-    float2 acc2[4][2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc2[j][0] = make_float2(0.f, 0.f); acc2[j][1] = make_float2(0.f, 0.f); }
-    const float* ap = AT + 4 * rg;
-    const float* wp = Ws + 4 * cg;
-    const int kbeg = half ? kh : 0, kend = half ? K : kh;
-#pragma unroll 4
-    for (int k = kbeg; k < kend; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(ap + k * BP);
-      const float4 wv = *reinterpret_cast<const float4*>(wp + k * W4);
-      const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
-      const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 ww = make_float2(wj[j], wj[j]);
-        acc2[j][0] = __ffma2_rn(ww, a01, acc2[j][0]);
-        acc2[j][1] = __ffma2_rn(ww, a23, acc2[j][1]);
-      }
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[j][0] = acc2[j][0].x; acc[j][1] = acc2[j][0].y; acc[j][2] = acc2[j][1].x; acc[j][3] = acc2[j][1].y; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[j][r] += __shfl_xor_sync(0xffffffffu, acc[j][r], 1);
-    if (!live || half) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = 4 * cg + j;
-      if (col >= w) continue;
-      const float bias = add_g ? add_g[o0 + col] : 0.f;
-      float o[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float v = acc[j][r] + bias;
-        if (relu) v = fmaxf(v, 0.f);
-        if (maskT) v = maskT[(o0 + col) * BP + 4 * rg + r] > 0.f ? v : 0.f;
-        if (4 * rg + r >= B) v = 0.f;
-        o[r] = v;
-      }
-      *reinterpret_cast<float4*>(outT_g + (size_t)(o0 + col) * BP + 4 * rg) = make_float4(o[0], o[1], o[2], o[3]);
-    }
+    gemm_task(g, tt0 + (int)threadIdx.x, ntile, NG);
   }
 }
 
 // Ws[k][j] = Wg[k*N + c0 + j]  (forward / dW column slice), zero padded to W4
-__device__ __forceinline__ void stage_w_cols(float* Ws, const float* Wg, int K, int N, int c0, int w, int W4) {
-  for (int idx = threadIdx.x; idx < K * W4; idx += kMT) {
-    const int k = idx / W4, j = idx - k * W4;
+// (t, nthr): the copying threads and their count (default: the whole CTA)
+__device__ __forceinline__ void stage_w_cols(float* Ws, const float* Wg, int K, int N, int c0, int w, int W4,
+                                             int t = threadIdx.x, int nthr = kMT) {
+  const float inv = 1.0f / (float)W4;
+  for (int idx = t; idx < K * W4; idx += nthr) {
+    const int k = fast_div(idx, inv), j = idx - k * W4;
     if (j < w) cp_async4(Ws + idx, Wg + (size_t)k * N + c0 + j); else Ws[idx] = 0.f;
   }
 }
 // Ws[n][j] = Wg[(k0+j)*N + n]   (dX: rows k0..k0+w of W, transposed), zero padded to W4
-__device__ __forceinline__ void stage_w_rows_t(float* Ws, const float* Wg, int N, int k0, int w, int W4) {
-  for (int idx = threadIdx.x; idx < W4 * N; idx += kMT) {
-    const int j = idx / N, n = idx - j * N;
+__device__ __forceinline__ void stage_w_rows_t(float* Ws, const float* Wg, int N, int k0, int w, int W4,
+                                               int t = threadIdx.x, int nthr = kMT) {
+  const float inv = 1.0f / (float)N;
+  for (int idx = t; idx < W4 * N; idx += nthr) {
+    const int j = fast_div(idx, inv), n = idx - j * N;
     if (j < w) cp_async4(Ws + n * W4 + j, Wg + (size_t)(k0 + j) * N + n); else Ws[n * W4 + j] = 0.f;
   }
 }
@@ -170,59 +228,64 @@ __device__ __forceinline__ void stage_w_rows_t(float* Ws, const float* Wg, int N
 // dWs[k][j] = sum_b HT[k][b] * dYT[c0+j][b]  (k < K, j < w);  dbs[j] = sum_b dYT[c0+j][b]
 // 4x4 tiles over (k, j); the 4 k-rows of a tile are interleaved (k, k+KT, k+2KT, k+3KT) so
 // the 128-bit loads of a warp's consecutive tiles hit consecutive bank groups.
+__device__ __forceinline__ void dw_task(int tile, const float* __restrict__ HT, int K, const float* __restrict__ dYT,
+                                        int c0, int w, int W4, float* __restrict__ dWs, int BP) {
+  const int KT = (K + 3) >> 2, NG = BP >> 2;
+  const int cg = tile / KT, kg = tile - cg * KT;
+  const float* hp[4]; const float* dp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hp[i] = HT + (size_t)min(kg + i * KT, K - 1) * BP;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dp[j] = dYT + (size_t)(c0 + min(4 * cg + j, w - 1)) * BP;
+  // FFMA2: each accumulator is a pair over the (x, y) / (z, w) halves of the 128-bit batch loads
+  // (even and odd batch columns are summed separately, then added)
+  float2 acc2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+  for (int g = 0; g < NG; ++g) {
+    float4 hv[4], dv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(hp[i] + 4 * g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dv[j] = *reinterpret_cast<const float4*>(dp[j] + 4 * g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 a = acc2[i][j];
+        a = __ffma2_rn(make_float2(hv[i].x, hv[i].y), make_float2(dv[j].x, dv[j].y), a);
+        a = __ffma2_rn(make_float2(hv[i].z, hv[i].w), make_float2(dv[j].z, dv[j].w), a);
+        acc2[i][j] = a;
+      }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = kg + i * KT;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * cg + j < w) dWs[k * W4 + 4 * cg + j] = acc[i][j];
+  }
+}
+// bias gradient of output column c0 + j
+__device__ __forceinline__ float db_col(const float* __restrict__ dYT, int c0, int j, int BP) {
+  const float* dp = dYT + (size_t)(c0 + j) * BP;
+  float a = 0.f;
+  for (int b = 0; b < BP; ++b) a += dp[b];
+  return a;
+}
 __device__ __forceinline__ void tile_dw(const float* __restrict__ HT, int K, const float* __restrict__ dYT, int c0, int w,
                                         int W4, float* __restrict__ dWs, float* __restrict__ dbs, int BP) {
-  const int KT = (K + 3) >> 2, ncg = W4 >> 2, NG = BP >> 2;
-  for (int tile = threadIdx.x; tile < KT * ncg; tile += kMT) {
-    const int cg = tile / KT, kg = tile - cg * KT;
-    const float* hp[4]; const float* dp[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) hp[i] = HT + (size_t)min(kg + i * KT, K - 1) * BP;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dp[j] = dYT + (size_t)(c0 + min(4 * cg + j, w - 1)) * BP;
-    // FFMA2: each accumulator is a pair over the (x, y) / (z, w) halves of the 128-bit batch loads
-    // (even and odd batch columns are summed separately, then added)
-    float2 acc2[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
-    for (int g = 0; g < NG; ++g) {
-      float4 hv[4], dv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(hp[i] + 4 * g);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dv[j] = *reinterpret_cast<const float4*>(dp[j] + 4 * g);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 a = acc2[i][j];
-          a = __ffma2_rn(make_float2(hv[i].x, hv[i].y), make_float2(dv[j].x, dv[j].y), a);
-          a = __ffma2_rn(make_float2(hv[i].z, hv[i].w), make_float2(dv[j].z, dv[j].w), a);
-          acc2[i][j] = a;
-        }
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = kg + i * KT;
-      if (k >= K) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (4 * cg + j < w) dWs[k * W4 + 4 * cg + j] = acc[i][j];
-    }
-  }
-  for (int j = threadIdx.x; j < w; j += kMT) {
-    const float* dp = dYT + (size_t)(c0 + j) * BP;
-    float a = 0.f;
-    for (int b = 0; b < BP; ++b) a += dp[b];
-    dbs[j] = a;
-  }
+  const int KT = (K + 3) >> 2, ncg = W4 >> 2;
+  for (int tile = threadIdx.x; tile < KT * ncg; tile += kMT) dw_task(tile, HT, K, dYT, c0, w, W4, dWs, BP);
+  for (int j = threadIdx.x; j < w; j += kMT) dbs[j] = db_col(dYT, c0, j, BP);
 }
 
 struct MlpHyper { float lr, b1, b2, omb1, omb2, eps, ibc1, ibc2; };
@@ -240,7 +303,8 @@ constexpr int kAB = 8;
 __device__ __forceinline__ void adam_slice(const MlpJobDev& J, int w_off, int b_off, int K, int N, int c0, int w, int W4,
                                            const float* dWs, const float* dbs, const MlpHyper& h) {
   float* __restrict__ P = J.params; float* __restrict__ M = J.adam_m; float* __restrict__ V = J.adam_v;
-  const int total = K * w;
+  const int total = (K + 1) * w;                 // row K of the slice is the bias: one batched pass, one L2 round trip
+  const float inv_w = 1.0f / (float)(w > 0 ? w : 1);
   for (int base = 0; base < total; base += kAB * kMT) {
     size_t gi[kAB]; float p[kAB], m[kAB], v[kAB], g[kAB]; bool ok[kAB];
 #pragma unroll
@@ -248,9 +312,9 @@ __device__ __forceinline__ void adam_slice(const MlpJobDev& J, int w_off, int b_
       const int idx = base + u * kMT + (int)threadIdx.x;
       ok[u] = idx < total;
       const int ii = ok[u] ? idx : 0;
-      const int k = ii / w, j = ii - k * w;
-      gi[u] = (size_t)w_off + (size_t)k * N + c0 + j;
-      g[u] = dWs[k * W4 + j];
+      const int k = fast_div(ii, inv_w), j = ii - k * w;
+      gi[u] = k < K ? (size_t)w_off + (size_t)k * N + c0 + j : (size_t)b_off + c0 + j;
+      g[u] = k < K ? dWs[k * W4 + j] : dbs[j];
       p[u] = __ldcg(P + gi[u]); m[u] = __ldcg(M + gi[u]); v[u] = __ldcg(V + gi[u]);
     }
 #pragma unroll
@@ -263,7 +327,6 @@ __device__ __forceinline__ void adam_slice(const MlpJobDev& J, int w_off, int b_
       }
     }
   }
-  for (int j = threadIdx.x; j < w; j += kMT) adam_one(P, M, V, (size_t)b_off + c0 + j, dbs[j], h);
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red) {   // result valid in every thread
@@ -277,6 +340,53 @@ __device__ __forceinline__ float block_sum(float v, float* red) {   // result va
   return t;
 }
 
+// Dense layers in execution order (overlapped schedule of the kernel, see "dual" below).
+// forward q: encoder 0 .. n_enc-1, then decoder 0 .. n_dec-1; backward r: decoder n_dec-1 .. 0, then encoder n_enc-1 .. 0.
+struct LayerRef {
+  int K, N, w_off, b_off, i;
+  const float* in_g;      // layer input in the workspace ([K][BP]); nullptr: the batch (encoder 0) / zs (decoder 0), in smem
+  float* out_g;           // forward output in the workspace ([N][BP])
+  bool relu, is_dec;
+};
+__device__ __forceinline__ LayerRef layer_ref(const MlpJobDev& J, float* ws, bool is_dec, int i) {
+  LayerRef r;
+  r.is_dec = is_dec; r.i = i;
+  if (!is_dec) {
+    r.K = i == 0 ? J.DR : J.enc_sizes[i]; r.N = J.enc_sizes[i + 1]; r.w_off = J.enc_w[i]; r.b_off = J.enc_b[i];
+    r.in_g = i > 0 ? ws + J.ws_enc[i - 1] : nullptr; r.out_g = ws + J.ws_enc[i]; r.relu = i + 1 < J.n_enc;
+  } else {
+    r.K = J.dec_sizes[i]; r.N = J.dec_sizes[i + 1]; r.w_off = J.dec_w[i]; r.b_off = J.dec_b[i];
+    r.in_g = i > 0 ? ws + J.ws_dec[i - 1] : nullptr; r.out_g = ws + J.ws_dec[i]; r.relu = i + 1 < J.n_dec;
+  }
+  return r;
+}
+__device__ __forceinline__ LayerRef fwd_ref(const MlpJobDev& J, float* ws, int q) {
+  return q < J.n_enc ? layer_ref(J, ws, false, q) : layer_ref(J, ws, true, q - J.n_enc);
+}
+__device__ __forceinline__ LayerRef bwd_ref(const MlpJobDev& J, float* ws, int r) {
+  return r < J.n_dec ? layer_ref(J, ws, true, J.n_dec - 1 - r) : layer_ref(J, ws, false, J.n_enc - 1 - (r - J.n_dec));
+}
+__device__ __forceinline__ uint32_t dynamic_smem_bytes() { uint32_t r; asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(r)); return r; }
+
+// -DVAE_MLP_TIMING: thread 0 of the first and of the last CTA of cluster 0 accumulate clock64() intervals per category
+// (scratch/mlp_timing.py reads them through vae_mlp_timing): where a step's time goes, as one CTA sees it.
+#ifdef VAE_MLP_TIMING
+enum { kTR = 0, kTFwdLoad, kTFwdGemm, kTFwdBar, kTOut, kTBwdFirstLoad, kTBwdTiles, kTBwdBar, kTBwdIssue, kTBwdAdam, kTBwdWait, kTLatent, kTTop, kTN };
+__device__ unsigned long long g_mlp_t[2][16];
+#define MLP_T0() long long t_mark = clock64()
+#define MLP_T(cat) do { if (tid == 0 && blockIdx.x < (unsigned)CS && (rank == 0 || rank == CS - 1)) { \
+    const long long t_now = clock64(); g_mlp_t[rank == 0 ? 0 : 1][cat] += (unsigned long long)(t_now - t_mark); t_mark = t_now; } } while (0)
+extern "C" int vae_mlp_timing(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  int rc = (int)cudaMemcpyFromSymbol(out32, g_mlp_t, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; rc |= (int)cudaMemcpyToSymbol(g_mlp_t, z, sizeof(z)); }
+  return rc;
+}
+#else
+#define MLP_T0() do {} while (0)
+#define MLP_T(cat) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kMT, 1)
 fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   extern __shared__ __align__(16) float sm[];
@@ -284,6 +394,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   __shared__ float red[kMT / 32];
   __shared__ uint32_t keys[8];
   __shared__ float sl_s[64], scal_s[4];
+  __shared__ __align__(8) uint64_t mbar;          // completion of the bulk operand copies (overlapped schedule)
   const int tid = threadIdx.x;
   const int rank = (int)cluster_ctarank(), CS = (int)cluster_nctarank();
   {
@@ -306,7 +417,21 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   float* z1T = xT + (size_t)DR * BP;              // [L][BP]
   float* muT = z1T + (size_t)L * BP;              // [L][BP]
   float* zsT = muT + (size_t)L * BP;              // [L][BP]
+  float* Ws2 = zsT + (size_t)L * BP;              // [maxw][W4max]  second staging buffer (overlapped schedule only)
   float* ws = J.ws;
+  // Overlapped schedule ("dual"): with one column slice per CTA (NP == 1) and room for a second staging buffer
+  // (mlp_smem_bytes(.., dual); the host grants it unless VAE_MLP_DUAL=0), every backward layer runs its dX tiles and its
+  // dW tiles SIDE BY SIDE on different warps (each alone occupies 7 of the 16 warps of a 16-CTA cluster), and the
+  // operands of the next layer -- its input activations, its transposed weight rows, the next dY -- are fetched while
+  // Adam updates this layer's slice; forward layers stage the next layer's weight slice while they multiply.  The
+  // arithmetic of every output element is that of the sequential schedule: results are bit-identical.
+  const int SLd = SL < 8 ? SL : 8;
+  const int W4d = m_up4((J.maxw + SLd - 1) / SLd);
+  const bool dual = CS >= kMlpBigCluster &&       // measured: no gain at 8 CTAs (two rounds of tiles per layer)
+      dynamic_smem_bytes() >= 4u * (uint32_t)(2 * J.maxw * BP + 2 * J.maxw * W4d + W4d + DR * BP + 3 * L * BP);
+  float* Wsb[2] = {Ws, Ws2};
+  uint32_t mph = 0;                               // phase parity of mbar (uniform: every thread waits on every copy)
+  if (tid == 0) m_mbar_init(&mbar, 1);            // ordered before its first use by the barriers below
   for (int i = tid; i < DR * BP; i += kMT) xT[i] = 0.f;
 
   // key chains (every CTA tracks both redundantly; lanes 0,1 model side, lanes 2,3 dataset side)
@@ -326,6 +451,7 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
   const bool decay_skipped = __syncthreads_or(nz) != 0;
   cluster_barrier();
 
+  MLP_T0();
   for (int64_t s = 0; s < n_steps; ++s) {
     // ---- keys of this step (vae.py:125, datasets.py:51)
     if (tid < 4) {
@@ -345,6 +471,12 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       scal_s[0] = e; scal_s[1] = expf(0.5f * e); scal_s[2] = expf(-e);
     }
     __syncthreads();
+    if (dual) {     // weight slice of the first forward layer: in flight during the draws (own columns: written by this CTA only)
+      const LayerRef f0 = fwd_ref(J, ws, 0);
+      const Slice s0 = slice_of(f0.N, rank, SL);
+      stage_w_cols(Wsb[0], J.params + f0.w_off, f0.K, f0.N, s0.c0, s0.w, m_up4(s0.w));
+    }
+    MLP_T(kTTop);
     // ================= phase R: random draws, spread over the whole cluster
     {
       const uint32_t lk0 = keys[0], lk1 = keys[1], bk0 = keys[2], bk1 = keys[3];
@@ -389,43 +521,87 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       }
     }
     __syncthreads();
-    // ================= encoder forward
-    for (int i = 0; i < J.n_enc; ++i) {
-      const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
-      const float* AT = xT;
-      if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); AT = bufA; }
-      for (int p = 0; p < NP; ++p) {
-        const Slice sc = slice_of(N, rank + p * CS, SL);
-        const int W4 = m_up4(sc.w);
-        if (p > 0) __syncthreads();                              // the previous pass has finished with Ws
-        stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
-        cp_async_wait_all(); __syncthreads();
-        tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
+    MLP_T(kTR);
+    const int NLf = J.n_enc + J.n_dec;
+    if (dual) {
+      // ================= forward, overlapped schedule: layer q multiplies out of Wsb[q & 1] while the weight slice of
+      // layer q + 1 (or the transposed rows the first backward layer needs) lands in the other buffer
+      for (int q = 0; q < NLf; ++q) {
+        const LayerRef r = fwd_ref(J, ws, q);
+        if (q == J.n_enc) {   // reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
+          load_rows(muT, ws + J.ws_enc[J.n_enc - 1], L, BP);
+          cp_async_wait_all(); __syncthreads();
+          for (int i = tid; i < L * BP; i += kMT) {
+            const int l = i / BP, b = i - l * BP;
+            zsT[i] = b < B ? fmaf(sl_s[l], z1T[i], muT[i]) : 0.f;
+          }
+        }
+        const float* AT = r.in_g ? bufA : (r.is_dec ? zsT : xT);
+        if (r.in_g && tid == 0) { m_expect_tx(&mbar, (uint32_t)(r.K * BP) * 4u); bulk_rows(bufA, r.in_g, r.K, BP, &mbar); }
+        const Slice sc = slice_of(r.N, rank, SL);
+        cp_async_wait_all();
+        if (r.in_g) { m_mbar_wait(&mbar, mph); mph ^= 1u; }
+        __syncthreads();
+        MLP_T(kTFwdLoad);
+        // the warps without GEMM tiles (9 of 16 at a 13-column slice) issue the copies; the others start multiplying
+        const int gw = min(kMT, (2 * (m_up4(sc.w) >> 2) * (BP >> 2) + 31) & ~31);
+        const int st0 = kMT - gw >= 64 ? gw : 0, snt = kMT - st0;
+        if (tid >= st0) {
+          if (q + 1 < NLf) {
+            const LayerRef nx = fwd_ref(J, ws, q + 1);
+            const Slice sn = slice_of(nx.N, rank, SL);
+            stage_w_cols(Wsb[(q + 1) & 1], J.params + nx.w_off, nx.K, nx.N, sn.c0, sn.w, m_up4(sn.w), tid - st0, snt);
+          } else {
+            const LayerRef nx = bwd_ref(J, ws, 0);
+            const Slice nk = slice_of(nx.K, rank, SL);
+            stage_w_rows_t(Wsb[NLf & 1], J.params + nx.w_off, nx.N, nk.c0, nk.w, m_up4(nk.w), tid - st0, snt);
+          }
+        }
+        tile_gemm(AT, r.K, Wsb[q & 1], m_up4(sc.w), sc.w, J.params + r.b_off, sc.c0, r.relu, nullptr, r.out_g, BP, B);
+        MLP_T(kTFwdGemm);
+        fence_async_global();
+        cluster_barrier();
+        MLP_T(kTFwdBar);
       }
-      cluster_barrier();
-    }
-    // ---- reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
-    load_rows(muT, ws + J.ws_enc[J.n_enc - 1], L, BP);
-    cp_async_wait_all(); __syncthreads();
-    for (int i = tid; i < L * BP; i += kMT) {
-      const int l = i / BP, b = i - l * BP;
-      zsT[i] = b < B ? fmaf(sl_s[l], z1T[i], muT[i]) : 0.f;
-    }
-    __syncthreads();
-    // ================= decoder forward
-    for (int i = 0; i < J.n_dec; ++i) {
-      const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
-      const float* AT = zsT;
-      if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); AT = bufA; }
-      for (int p = 0; p < NP; ++p) {
-        const Slice sc = slice_of(N, rank + p * CS, SL);
-        const int W4 = m_up4(sc.w);
-        if (p > 0) __syncthreads();
-        stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
-        cp_async_wait_all(); __syncthreads();
-        tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
+    } else {
+      // ================= encoder forward
+      for (int i = 0; i < J.n_enc; ++i) {
+        const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
+        const float* AT = xT;
+        if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); AT = bufA; }
+        for (int p = 0; p < NP; ++p) {
+          const Slice sc = slice_of(N, rank + p * CS, SL);
+          const int W4 = m_up4(sc.w);
+          if (p > 0) __syncthreads();                              // the previous pass has finished with Ws
+          stage_w_cols(Ws, J.params + J.enc_w[i], K, N, sc.c0, sc.w, W4);
+          cp_async_wait_all(); __syncthreads();
+          tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.enc_b[i], sc.c0, i + 1 < J.n_enc, nullptr, ws + J.ws_enc[i], BP, B);
+        }
+        cluster_barrier();
       }
-      cluster_barrier();
+      // ---- reparameterise (every CTA, all rows): zs = mu + exp(lv/2) * z1   (networks.py:73-74)
+      load_rows(muT, ws + J.ws_enc[J.n_enc - 1], L, BP);
+      cp_async_wait_all(); __syncthreads();
+      for (int i = tid; i < L * BP; i += kMT) {
+        const int l = i / BP, b = i - l * BP;
+        zsT[i] = b < B ? fmaf(sl_s[l], z1T[i], muT[i]) : 0.f;
+      }
+      __syncthreads();
+      // ================= decoder forward
+      for (int i = 0; i < J.n_dec; ++i) {
+        const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
+        const float* AT = zsT;
+        if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); AT = bufA; }
+        for (int p = 0; p < NP; ++p) {
+          const Slice sc = slice_of(N, rank + p * CS, SL);
+          const int W4 = m_up4(sc.w);
+          if (p > 0) __syncthreads();
+          stage_w_cols(Ws, J.params + J.dec_w[i], K, N, sc.c0, sc.w, W4);
+          cp_async_wait_all(); __syncthreads();
+          tile_gemm(AT, K, Ws, W4, sc.w, J.params + J.dec_b[i], sc.c0, i + 1 < J.n_dec, nullptr, ws + J.ws_dec[i], BP, B);
+        }
+        cluster_barrier();
+      }
     }
     // ================= output, loss, d x_hat (every CTA, all rows; reductions used by CTA 0)
     {
@@ -464,82 +640,167 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
       }
       __syncthreads();
     }
-    // ================= decoder backward (dY^T of layer i in bufB, all N rows)
-    int pp = 0;
-    for (int i = J.n_dec - 1; i >= 0; --i) {
-      const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
-      const float* HT = zsT;
-      if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); HT = bufA; }
-      // dX slices: rows k0..k0+kw of the layer input
-      float* dst = i > 0 ? ws + J.ws_g[pp] : ws + J.ws_dzs;
-      for (int p = 0; p < NP; ++p) {
-        const Slice sk = slice_of(K, rank + p * CS, SL);
-        const int K4 = m_up4(sk.w);
-        if (p > 0) __syncthreads();
-        stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
-        cp_async_wait_all(); __syncthreads();
-        tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
+    MLP_T(kTOut);
+    if (dual) {
+      // ================= backward, overlapped schedule (dY^T of the layer in bufB, all N rows)
+      float* WsX = Wsb[NLf & 1];          // transposed weight rows of the dX product (staged one layer ahead)
+      float* WsD = Wsb[(NLf - 1) & 1];    // dW slice of this layer, read by Adam
+      const int NG = BP >> 2;
+      {
+        const LayerRef c0 = bwd_ref(J, ws, 0);
+        if (c0.in_g && tid == 0) { m_expect_tx(&mbar, (uint32_t)(c0.K * BP) * 4u); bulk_rows(bufA, c0.in_g, c0.K, BP, &mbar); }
+        cp_async_wait_all();
+        if (c0.in_g) { m_mbar_wait(&mbar, mph); mph ^= 1u; }
+        __syncthreads();
       }
-      __syncthreads();
-      // dW slices: columns c0..c0+w of the layer output.  Adam may only start once every CTA has
-      // finished reading this layer's weights (the barrier); the first slice's dW is formed before it.
-      for (int p = 0; p < NP; ++p) {
-        const Slice sc = slice_of(N, rank + p * CS, SL);
-        const int W4 = m_up4(sc.w);
-        if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
-        if (p == 0) cluster_barrier(); else __syncthreads();
-        if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
-        adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
-        if (NP > 1) __syncthreads();
-      }
-      if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }       // bufB was still this layer's dY^T
-      cp_async_wait_all(); __syncthreads();
-    }
-    // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
-    load_rows(bufB, ws + J.ws_dzs, L, BP);
-    cp_async_wait_all(); __syncthreads();
-    if (rank == 0) {
-      // g_lv[l] = sum_b dzs*z1 * 0.5*s_l - 0.5*(1 - e^lv_l): one warp per l
-      for (int l = tid >> 5; l < L; l += kMT / 32) {
-        float a = 0.f;
-        for (int b = tid & 31; b < B; b += 32) a = fmaf(bufB[l * BP + b], z1T[l * BP + b], a);
-        a = warp_sum(a);
-        if ((tid & 31) == 0) {
-          const float lv = __ldcg(J.params + J.off_lv + l);
-          adam_one(J.params, J.adam_m, J.adam_v, (size_t)J.off_lv + l, a * 0.5f * sl_s[l] - 0.5f * (1.f - expf(lv)), hp);
+      MLP_T(kTBwdFirstLoad);
+      int pp = 0;
+      for (int r = 0; r < NLf; ++r) {
+        const LayerRef c = bwd_ref(J, ws, r);
+        const bool has_dx = c.is_dec || c.i > 0;           // the encoder's first layer has no input gradient
+        const bool to_latent = c.is_dec && c.i == 0;       // dX of the decoder's first layer is dzs
+        const float* HT = c.in_g ? bufA : (c.is_dec ? zsT : xT);
+        const Slice sk = slice_of(c.K, rank, SL);          // dX: this CTA's rows of the layer input
+        const Slice sc = slice_of(c.N, rank, SL);          // dW + Adam: this CTA's output columns
+        const int K4 = m_up4(sk.w), W4 = m_up4(sc.w);
+        const GemmArgs g{bufB, c.N, WsX, K4, sk.w, nullptr, sk.c0, false, c.i > 0 ? HT : nullptr,
+                         to_latent ? ws + J.ws_dzs : ws + J.ws_g[pp], BP, B};
+        const int ntile = (K4 >> 2) * NG;
+        const int nG = has_dx ? (2 * ntile + 31) & ~31 : 0;            // whole warps of dX tasks, then the dW tiles
+        const int nD = sc.w > 0 ? ((c.K + 3) >> 2) * (W4 >> 2) : 0;
+        for (int base = 0; base < nG + nD; base += kMT) {
+          const int wt = base + (tid & ~31);                           // warp-uniform
+          if (wt >= nG + nD) break;
+          if (wt < nG) {
+            gemm_task(g, base + tid, ntile, NG);
+          } else {
+            const int tile = base + tid - nG;
+            if (tile < nD) dw_task(tile, HT, c.K, bufB, sc.c0, sc.w, W4, WsD, BP);
+          }
+        }
+        { const int j = kMT - 1 - tid; if (j < sc.w) dbs[j] = db_col(bufB, sc.c0, j, BP); }   // the last warps idle above
+        MLP_T(kTBwdTiles);
+        // Adam may only start once every CTA has finished reading this layer's weights (the barrier)
+        if (has_dx) { fence_async_global(); cluster_barrier(); } else __syncthreads();
+        MLP_T(kTBwdBar);
+        if (r + 1 < NLf) {     // operands of the next layer, in flight during Adam
+          const LayerRef nx = bwd_ref(J, ws, r + 1);
+          if (tid == 0) {
+            const int nb = to_latent ? L : c.K;
+            m_expect_tx(&mbar, (uint32_t)((nb + (nx.in_g ? nx.K : 0)) * BP) * 4u);
+            bulk_rows(bufB, to_latent ? ws + J.ws_dzs : ws + J.ws_g[pp], nb, BP, &mbar);
+            if (nx.in_g) bulk_rows(bufA, nx.in_g, nx.K, BP, &mbar);
+          }
+          if (!to_latent) pp ^= 1;
+          if (nx.is_dec || nx.i > 0) {
+            const Slice nk = slice_of(nx.K, rank, SL);
+            stage_w_rows_t(WsX, J.params + nx.w_off, nx.N, nk.c0, nk.w, m_up4(nk.w));
+          }
+        }
+        MLP_T(kTBwdIssue);
+        adam_slice(J, c.w_off, c.b_off, c.K, c.N, sc.c0, sc.w, W4, WsD, dbs, hp);
+        MLP_T(kTBwdAdam);
+        cp_async_wait_all();
+        if (r + 1 < NLf) { m_mbar_wait(&mbar, mph); mph ^= 1u; }
+        __syncthreads();
+        MLP_T(kTBwdWait);
+        if (to_latent) {
+          // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
+          if (rank == 0) {
+            for (int l = tid >> 5; l < L; l += kMT / 32) {
+              float a = 0.f;
+              for (int b = tid & 31; b < B; b += 32) a = fmaf(bufB[l * BP + b], z1T[l * BP + b], a);
+              a = warp_sum(a);
+              if ((tid & 31) == 0) {
+                const float lv = __ldcg(J.params + J.off_lv + l);
+                adam_one(J.params, J.adam_m, J.adam_v, (size_t)J.off_lv + l, a * 0.5f * sl_s[l] - 0.5f * (1.f - expf(lv)), hp);
+              }
+            }
+          }
+          __syncthreads();
+          for (int i = tid; i < L * BP; i += kMT) { const int b = i % BP; bufB[i] = b < B ? fmaf(muT[i], invB, bufB[i]) : 0.f; }
+          __syncthreads();
+          MLP_T(kTLatent);
         }
       }
-    }
-    __syncthreads();
-    for (int i = tid; i < L * BP; i += kMT) { const int b = i % BP; bufB[i] = b < B ? fmaf(muT[i], invB, bufB[i]) : 0.f; }
-    __syncthreads();
-    // ================= encoder backward
-    for (int i = J.n_enc - 1; i >= 0; --i) {
-      const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
-      const float* HT = xT;
-      if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); HT = bufA; }
-      if (i > 0) {
+    } else {
+      // ================= decoder backward (dY^T of layer i in bufB, all N rows)
+      int pp = 0;
+      for (int i = J.n_dec - 1; i >= 0; --i) {
+        const int K = J.dec_sizes[i], N = J.dec_sizes[i + 1];
+        const float* HT = zsT;
+        if (i > 0) { load_rows(bufA, ws + J.ws_dec[i - 1], K, BP); HT = bufA; }
+        // dX slices: rows k0..k0+kw of the layer input
+        float* dst = i > 0 ? ws + J.ws_g[pp] : ws + J.ws_dzs;
         for (int p = 0; p < NP; ++p) {
           const Slice sk = slice_of(K, rank + p * CS, SL);
           const int K4 = m_up4(sk.w);
           if (p > 0) __syncthreads();
-          stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
+          stage_w_rows_t(Ws, J.params + J.dec_w[i], N, sk.c0, sk.w, K4);
           cp_async_wait_all(); __syncthreads();
-          tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
+          tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, i > 0 ? HT : nullptr, dst, BP, B);
         }
         __syncthreads();
+        // dW slices: columns c0..c0+w of the layer output.  Adam may only start once every CTA has
+        // finished reading this layer's weights (the barrier); the first slice's dW is formed before it.
+        for (int p = 0; p < NP; ++p) {
+          const Slice sc = slice_of(N, rank + p * CS, SL);
+          const int W4 = m_up4(sc.w);
+          if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+          if (p == 0) cluster_barrier(); else __syncthreads();
+          if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
+          adam_slice(J, J.dec_w[i], J.dec_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+          if (NP > 1) __syncthreads();
+        }
+        if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }       // bufB was still this layer's dY^T
+        cp_async_wait_all(); __syncthreads();
       }
-      for (int p = 0; p < NP; ++p) {
-        const Slice sc = slice_of(N, rank + p * CS, SL);
-        const int W4 = m_up4(sc.w);
-        if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
-        if (p == 0 && i > 0) cluster_barrier(); else __syncthreads();
-        if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
-        adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
-        if (NP > 1) __syncthreads();
-      }
-      if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
+      // ================= latent: d lv (CTA 0), dmu = dzs + mu / B  -> dY^T of the last encoder layer
+      load_rows(bufB, ws + J.ws_dzs, L, BP);
       cp_async_wait_all(); __syncthreads();
+      if (rank == 0) {
+        // g_lv[l] = sum_b dzs*z1 * 0.5*s_l - 0.5*(1 - e^lv_l): one warp per l
+        for (int l = tid >> 5; l < L; l += kMT / 32) {
+          float a = 0.f;
+          for (int b = tid & 31; b < B; b += 32) a = fmaf(bufB[l * BP + b], z1T[l * BP + b], a);
+          a = warp_sum(a);
+          if ((tid & 31) == 0) {
+            const float lv = __ldcg(J.params + J.off_lv + l);
+            adam_one(J.params, J.adam_m, J.adam_v, (size_t)J.off_lv + l, a * 0.5f * sl_s[l] - 0.5f * (1.f - expf(lv)), hp);
+          }
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < L * BP; i += kMT) { const int b = i % BP; bufB[i] = b < B ? fmaf(muT[i], invB, bufB[i]) : 0.f; }
+      __syncthreads();
+      // ================= encoder backward
+      for (int i = J.n_enc - 1; i >= 0; --i) {
+        const int K = i == 0 ? DR : J.enc_sizes[i], N = J.enc_sizes[i + 1];
+        const float* HT = xT;
+        if (i > 0) { load_rows(bufA, ws + J.ws_enc[i - 1], K, BP); HT = bufA; }
+        if (i > 0) {
+          for (int p = 0; p < NP; ++p) {
+            const Slice sk = slice_of(K, rank + p * CS, SL);
+            const int K4 = m_up4(sk.w);
+            if (p > 0) __syncthreads();
+            stage_w_rows_t(Ws, J.params + J.enc_w[i], N, sk.c0, sk.w, K4);
+            cp_async_wait_all(); __syncthreads();
+            tile_gemm(bufB, N, Ws, K4, sk.w, nullptr, sk.c0, false, HT, ws + J.ws_g[pp], BP, B);
+          }
+          __syncthreads();
+        }
+        for (int p = 0; p < NP; ++p) {
+          const Slice sc = slice_of(N, rank + p * CS, SL);
+          const int W4 = m_up4(sc.w);
+          if (sc.w > 0) tile_dw(HT, K, bufB, sc.c0, sc.w, W4, Ws, dbs, BP);
+          if (p == 0 && i > 0) cluster_barrier(); else __syncthreads();
+          if (NP == 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }     // next dY^T, in flight during Adam
+          adam_slice(J, J.enc_w[i], J.enc_b[i], K, N, sc.c0, sc.w, W4, Ws, dbs, hp);
+          if (NP > 1) __syncthreads();
+        }
+        if (NP > 1 && i > 0) { load_rows(bufB, ws + J.ws_g[pp], K, BP); pp ^= 1; }
+        cp_async_wait_all(); __syncthreads();
+      }
     }
     if (decay_skipped)
       for (int g = tid; g < skipN; g += kMT) adam_one(J.params, J.adam_m, J.adam_v, (size_t)skip0 + g, 0.f, hp);
@@ -553,9 +814,17 @@ fused_mlp_kernel(const MlpJobDev* __restrict__ jobs, int64_t n_steps) {
 }
 
 // ------------------------------------------------------------------------ host side
-static size_t mlp_smem_bytes(int maxw, int BP, int DR, int L, int cs) {
+// dual: with the second weight-staging buffer of the overlapped schedule (the kernel compares its dynamic
+// shared-memory size with exactly this figure at cs = 8, see "dual" in fused_mlp_kernel)
+static size_t mlp_smem_bytes(int maxw, int BP, int DR, int L, int cs, bool dual = false) {
   const int W4max = m_up4((maxw + cs - 1) / cs);
-  return sizeof(float) * ((size_t)2 * maxw * BP + (size_t)maxw * W4max + W4max + (size_t)DR * BP + (size_t)3 * L * BP);
+  return sizeof(float) * ((size_t)2 * maxw * BP + (size_t)(dual ? 2 : 1) * maxw * W4max + W4max + (size_t)DR * BP +
+                          (size_t)3 * L * BP);
+}
+// VAE_MLP_DUAL=0: sequential schedule (A/B runs); read once
+static bool mlp_dual_enabled() {
+  static const bool on = [] { const char* e = getenv("VAE_MLP_DUAL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 static size_t mlp_ws_floats(const Layout& Lo, const VaeDesc& d, const VaeDataDesc& g, MlpJobDev* o) {
@@ -593,7 +862,8 @@ int mlp_supported(const VaeTrainJob* j, size_t* smem, size_t* ws_bytes, size_t* 
   const int dr = g.dim + (g.kind == VAE_DATA_SIGMOID ? 1 : 0);
   const size_t sb = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpMaxCluster);
   if (sb > (size_t)227 * 1024 - 2048) return 0;
-  if (smem) *smem = sb;
+  const size_t sbd = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpMaxCluster, true);
+  if (smem) *smem = (mlp_dual_enabled() && sbd <= (size_t)227 * 1024 - 2048) ? sbd : sb;
   if (smem4) {      // 4-CTA clusters stage wider weight slices; 0 if that does not fit
     const size_t s4 = mlp_smem_bytes(Lo.max_width, BP, dr, d.latent_dim, kMlpSmallCluster);
     *smem4 = s4 > (size_t)227 * 1024 - 2048 ? 0 : s4;

@@ -37,6 +37,11 @@ constexpr int kGroupBatch = 100;      // batch size the GM > 1 kernels are compi
 #ifndef VAE_SMALL_MAXB
 #define VAE_SMALL_MAXB 8
 #endif
+// 1: the models of a CTA that share an eps stream (GM > 1) keep ONE copy of it, in the z buffer of the group's
+// lowest-numbered model, instead of storing every normal into each member's buffer (see "Shared eps draw")
+#ifndef VAE_SMALL_LEADZ
+#define VAE_SMALL_LEADZ 1
+#endif
 
 struct FusedJobDev {
   float* params; float* adam_m; float* adam_v; int32_t* step;
@@ -199,10 +204,21 @@ __device__ __noinline__ void small_draw(float* zdst, float* gdst, const uint32_t
     const int o0 = off_of(ja), o1 = off_of(v1 ? ja + half : ja), o2 = off_of(vb ? jb : ja), o3 = off_of(v3 ? jb + half : ja);
     if (isd || mode == 0) {
       float* dst = isd ? gdst : zdst;
-      dst[o0] = n0;
-      if (v1) dst[o1] = n1;
-      if (vb) dst[o2] = n2;
-      if (v3) dst[o3] = n3;
+#if VAE_SMALL_LEADZ
+      // contiguous rows (odd L + D, odd G) and an even half: the normals of blocks (ja, ja + 1) are neighbours in
+      // both halves of the array -> two 64-bit stores (ja is even, the buffers are 16-byte aligned)
+      const bool lin = isd ? C::SG == G : C::SZ == LD;
+      if (lin && v3 && (half & 1) == 0) {
+        *reinterpret_cast<float2*>(dst + ja) = make_float2(n0, n2);
+        *reinterpret_cast<float2*>(dst + ja + half) = make_float2(n1, n3);
+      } else
+#endif
+      {
+        dst[o0] = n0;
+        if (v1) dst[o1] = n1;
+        if (vb) dst[o2] = n2;
+        if (v3) dst[o3] = n3;
+      }
     } else if (mode == 2) {           // the same four stores into the z of every group member of this CTA
       for (uint32_t m = gmask; m; m &= m - 1u) {
         float* dst = zdst + ((__ffs((int)m) - 1) - mi) * mstride;
@@ -348,7 +364,11 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     }
   }
   const int gsize = __popc(gmask), gidx = __popc(gmask & ((1u << self) - 1u));
-  const int draw_mode = gsize == 1 ? 0 : GM > 1 ? 2 : 1;
+  constexpr bool kLeadZ = VAE_SMALL_LEADZ != 0 && GM > 1;
+  const int draw_mode = gsize == 1 || kLeadZ ? 0 : GM > 1 ? 2 : 1;
+  // kLeadZ: the group's eps is stored once, into its lowest-numbered member's z; every member reads it there
+  const int lead = kLeadZ ? __ffs((int)gmask) - 1 : mi;
+  if (kLeadZ && t == 0) reinterpret_cast<int*>(sm + y.red)[13] = lead;
   __syncthreads();
   SMALL_STAMP(3);
 
@@ -365,7 +385,8 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   // key chains for step q+1 into the other slot
   auto draw_step = [&](int64_t q) {
     const int qs = (int)(q & 1), buf = pipe ? qs : 0;
-    small_draw<C>(sm + y.z + buf * zstride, sm + y.gn + buf * gstride, keys + qs * 4, B, e_lo, e_hi, gmask, draw_mode, t, mi, y.total);
+    small_draw<C>((kLeadZ ? sm_cta + lead * y.total : sm) + y.z + buf * zstride, sm + y.gn + buf * gstride, keys + qs * 4, B, e_lo, e_hi,
+                  gmask, draw_mode, t, mi, y.total);
     if (t < 4 && q + 1 < n_steps) advance_keys(qs ^ 1);
   };
   if (pipe) {
@@ -389,13 +410,14 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
     const int mb = tail_warp ? ((t - 96) >> 2) & 3 : mi;                       // the model whose row this thread works on
     float* smB = tail_warp ? sm_cta + mb * y.total : sm;
     const float* Pb = smB + y.P;
+    const float* zB = !kLeadZ ? smB + y.z : sm_cta + (tail_warp ? reinterpret_cast<const int*>(smB + y.red)[13] : lead) * y.total + y.z;
     const int b_first = !tail_warp ? t : (mi == 0 && t < 112) ? 96 + ((t - 96) & 3) : B;
     float kl_acc = 0.f, r2_acc = 0.f, rz_acc = 0.f;
     {
       const float sd = smB[y.scal + 8 * slot + 1], inv_var = smB[y.scal + 8 * slot + 2];
       const float gscale = inv_var * invB;
       for (int b = b_first; b < B; b += kT) {
-        const float* zr = smB + y.z + zb * zstride + b * C::SZ;
+        const float* zr = zB + zb * zstride + b * C::SZ;
         const float* gr = smB + y.gn + zb * gstride + b * C::SG;
         // ---- generator transform (bit-exact with oracle/datasets.py)
         float x[DR];
