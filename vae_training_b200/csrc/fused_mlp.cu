@@ -108,12 +108,9 @@ __device__ __forceinline__ void m_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // dst (smem, [nrows][BP]) <- src (global, same layout); call from ONE thread, after m_expect_tx of the total
 __device__ __forceinline__ void bulk_rows(float* dst, const float* src, int nrows, int BP, uint64_t* bar) {
-  const uint32_t bytes = (uint32_t)(nrows * BP) * 4u;
-  for (uint32_t off = 0; off < bytes; off += 32768u) {
-    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(m_smem(dst) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(m_smem(bar)) : "memory");
-  }
+  const uint32_t bytes = (uint32_t)(nrows * BP) * 4u;      // one copy per array (80 KB for a 200-wide layer); a multiple of 16
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(m_smem(dst)), "l"(src), "r"(bytes), "r"(m_smem(bar)) : "memory");
 }
 // This thread's global stores become visible to the async proxy (the peers' bulk copies after the next cluster barrier).
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
