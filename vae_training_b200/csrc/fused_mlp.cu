@@ -62,9 +62,11 @@ __device__ __forceinline__ void cluster_barrier() {
 __device__ __forceinline__ int fast_div(int idx, float inv_d) { return __float2int_rz(((float)idx + 0.5f) * inv_d); }
 
 struct Slice { int c0, w; };
+// Slices are dealt out from the LAST rank down: the short remainder slice (5 of 200 columns at 16 CTAs) lands on CTA 0,
+// which also computes the loss and the latent-variance update for the whole cluster.
 __device__ __forceinline__ Slice slice_of(int n, int rank, int cs) {
   const int chunk = (n + cs - 1) / cs;
-  int c0 = rank * chunk; if (c0 > n) c0 = n;
+  int c0 = (cs - 1 - rank) * chunk; if (c0 > n) c0 = n;
   int c1 = c0 + chunk; if (c1 > n) c1 = n;
   return Slice{c0, c1 - c0};
 }
