@@ -89,6 +89,62 @@ def test_init_params_distribution_and_layout():
     np.testing.assert_array_equal(p, init.init_params(spec, np.array([1, 2], np.uint32)))
 
 
+def test_init_rng_known_answers():
+    """The host threefry of init.py against the Random123 known answers and the documented split(PRNGKey(0))."""
+    import json
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "jax_random_kat.json")))
+    for v in kat["published"]["threefry2x32_kat"]:
+        with np.errstate(over="ignore"):
+            y0, y1 = init._threefry2x32(np.uint32(v["key"][0]), np.uint32(v["key"][1]),
+                                        np.array([v["ctr"][0]], np.uint32), np.array([v["ctr"][1]], np.uint32))
+        assert [int(y0[0]), int(y1[0])] == v["out"]
+    # fold_in(key, d) = threefry(key, [0, d]) in jax's array layout (lane 0 counter 0, lane 1 counter d)
+    key = np.array([0x243F6A88, 0x85A308D3], np.uint32)
+    with np.errstate(over="ignore"):
+        y0, y1 = init._threefry2x32(key[0], key[1], np.array([0], np.uint32), np.array([77], np.uint32))
+    np.testing.assert_array_equal(init.fold_in(key, 77), [y0[0], y1[0]])
+    # sha1("kernel")[:4] big endian (legacy flax _fold_in_str)
+    import hashlib
+    assert int.from_bytes(hashlib.sha1(b"kernel").digest()[:4], "big") == int(hashlib.sha1(b"kernel").hexdigest()[:8], 16)
+    np.testing.assert_array_equal(init.leaf_key(key, "Encoder/FC0/kernel"),
+                                  init.fold_in_str(init.fold_in_str(init.fold_in_str(key, "Encoder"), "FC0"), "kernel"))
+
+
+def test_truncated_normal_definition():
+    """jax.random.truncated_normal(key, -2, 2): inside the open interval, the distribution of a unit normal cut at 2 sigma."""
+    x = init.truncated_normal(np.array([5, 6], np.uint32), -2.0, 2.0, (300, 401))
+    assert x.dtype == np.float32 and x.shape == (300, 401)
+    assert x.min() > -2.0 and x.max() < 2.0
+    assert abs(float(x.mean())) < 0.01 and abs(float(x.std()) - 0.87962566) < 0.005
+    # odd element counts use jax's padded counter layout; a prefix of a longer draw is a different stream
+    y = init.truncated_normal(np.array([5, 6], np.uint32), -2.0, 2.0, (7,))
+    assert y.shape == (7,) and not np.array_equal(y, x.reshape(-1)[:7])
+
+
+REF_INIT_FIXTURES = ["ref_linear_dd3_pd9_ld20", "ref_linear_noise_dn", "ref_sigmoid_dd3_pd3_ld6",
+                     "ref_sigmoid_dd5_pd5_ld10_seed24", "ref_sphere_dd3_pd3_ld6", "ref_sphere_small_fixedvar"]
+
+
+@pytest.mark.parametrize("name", REF_INIT_FIXTURES)
+def test_init_params_reproduce_the_reference_init(name):
+    """`init_params` of the fixtures came out of the reference's OWN `VAE.init_by_shape(vae_key, ...)` (vae.py:56-60,
+    networks.py:36,63-77) executed on tests/refshim, whose flax.nn restates legacy flax's per-name key folding and
+    computes the truncated normal in float64.  The product's float32 init must land on the same values: same leaves in
+    the same order, same names folded, same key chain (vae_key = row 0 of split(PRNGKey(0)), model.py:29), same
+    distribution -- to float32 round-off (<= 5e-7 absolute on values of magnitude <= 1.3)."""
+    import dataclasses
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"), allow_pickle=False)
+    a = run.parse_arguments([str(x) for x in f["argv"]])
+    spec = dataclasses.replace(sweep._spec_of(a), tunable_decoder_var=a.tunable_decoder_var)
+    vae_key = init._threefry_counts(np.zeros(2, np.uint32), np.arange(4, dtype=np.uint32)).reshape(2, 2)[0]
+    got = init.init_params(spec, vae_key)
+    assert got.dtype == np.float32 and got.shape == f["init_params"].shape
+    assert np.abs(got.astype(np.float64) - f["init_params"]).max() <= 5e-7
+    # and a different module key gives different kernels (the fixture is not matched by accident)
+    other = init.init_params(spec, vae_key ^ np.uint32(1))
+    assert np.abs(other.astype(np.float64) - f["init_params"]).max() > 1e-2
+
+
 def test_checkpoint_roundtrip(tmp_path):
     spec = RunSpec("sigmoid", 3, 3, 6, tunable_decoder_var=True)
     rng = np.random.default_rng(0)

@@ -1,15 +1,26 @@
 """Initial state of a run: parameter init and the PRNG key chains up to the first training
 step.  Key chains, generator matrices and the warm-start perturbations come from the library's device RNG
-(bit-identical to jax.random); the random Dense kernels are drawn on the host with NumPy (see below).
+(bit-identical to jax.random); the random Dense kernels are drawn on the host (init is not on the hot path)
+from per-leaf keys derived the way legacy flax derives them.
 
-Parameter init follows the *distribution* legacy flax uses (vae.py:57-60; SURVEY.md
-Appendix D): Dense kernels lecun-normal (normal truncated at +-2 sigma, variance
-1/fan_in), biases zero, ``epsilon_p`` and ``epsilon`` ones (networks.py:69,71).  flax's
-per-leaf key derivation cannot be verified here, so values are NOT bit-identical to a
-flax run; the step itself takes parameters as an input.
+Parameter init (vae.py:57-60 -> ``VAE.init_by_shape(vae_key, ...)``):
+* per-leaf key: legacy ``flax.nn`` folds the SHA-1 of every submodule / parameter NAME into the parent's key
+  (``fold_in(key, int.from_bytes(sha1(name)[:4], "big"))``), so the kernel of ``Encoder/FC0`` is drawn with
+  ``fold(fold(fold(vae_key, "Encoder"), "FC0"), "kernel")`` -- the names are the reference's own
+  (networks.py:36,63-77);
+* Dense kernels: ``jax.nn.initializers.lecun_normal`` = ``random.truncated_normal(key, -2, 2, shape) *
+  sqrt(1 / fan_in) / 0.8796...``, restated in float32 the way jax computes it (uniform on
+  [erf(-sqrt 2), erf(sqrt 2)] from the threefry bits, ``sqrt2 * erf_inv(u)``, clamped to the open interval);
+* biases zero, ``epsilon_p`` and ``epsilon`` ones (networks.py:69,71).
+What pins it: the reference's own source run on tests/refshim (which restates the same flax rule) produced
+the ``init_params`` of tests/golden/ref_*.npz; tests/test_host_logic.py requires this module to reproduce them
+(leaf order, names, key folding, distribution).  What cannot be pinned offline: that real flax 0.2 / XLA agree
+with the recalled rule and with this erf_inv to the last bit -- the step itself takes parameters as an input.
 """
 from __future__ import annotations
 
+import hashlib
+import math
 from typing import Optional, Tuple
 
 import numpy as np
@@ -39,17 +50,103 @@ def layer_shapes(spec: RunSpec):
     return out
 
 
+# ---- host restatement of the few jax.random / flax pieces init needs (uint32 / float32 NumPy; ~2 k words per model)
+_U32 = np.uint32
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+
+def _threefry2x32(k0, k1, x0, x1):
+    """Threefry-2x32, 20 rounds (jax/_src/prng.py threefry2x32; Random123 known answers in tests/test_host_logic.py)."""
+    ks = (_U32(k0), _U32(k1), _U32(_U32(k0) ^ _U32(k1) ^ _U32(0x1BD11BDA)))
+    x0 = np.asarray(x0, _U32) + ks[0]
+    x1 = np.asarray(x1, _U32) + ks[1]
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = x0 + x1
+            x1 = (x1 << _U32(r)) | (x1 >> _U32(32 - r))
+            x1 = x1 ^ x0
+        x0 = x0 + ks[(i + 1) % 3]
+        x1 = x1 + ks[(i + 2) % 3] + _U32(i + 1)
+    return x0, x1
+
+
+def _threefry_counts(key, counts) -> np.ndarray:
+    """jax's array form: counters padded to an even length, first half in lane 0, second half in lane 1."""
+    counts = np.asarray(counts, _U32).ravel()
+    n = counts.size
+    if n % 2:
+        counts = np.concatenate([counts, np.zeros(1, _U32)])
+    h = counts.size // 2
+    with np.errstate(over="ignore"):
+        y0, y1 = _threefry2x32(key[0], key[1], counts[:h], counts[h:])
+    return np.concatenate([y0, y1])[:n]
+
+
+def fold_in(key, data: int) -> np.ndarray:
+    """``jax.random.fold_in(key, data)`` = threefry(key, PRNGKey(data))."""
+    return _threefry_counts(key, np.array([0, data & 0xFFFFFFFF], _U32))
+
+
+def fold_in_str(key, name: str) -> np.ndarray:
+    """legacy flax.nn ``_fold_in_str``: the first four bytes of the SHA-1 of the name, big endian."""
+    return fold_in(key, int.from_bytes(hashlib.sha1(name.encode("utf-8")).digest()[:4], byteorder="big"))
+
+
+# Giles' single-precision erf_inv (XLA ErfInv32), highest degree first
+_ERFINV_CENTRAL = [np.float32(c) for c in (2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087,
+                                           -0.00125372503, -0.00417768164, 0.246640727, 1.50140941)]
+_ERFINV_TAIL = [np.float32(c) for c in (-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773,
+                                        -0.0076224613, 0.00943887047, 1.00167406, 2.83297682)]
+
+
+def _erf_inv_f32(x: np.ndarray) -> np.ndarray:
+    F = np.float32
+    x = np.asarray(x, F)
+    w = -np.log1p(-(x * x)).astype(F)
+    small = w < F(5.0)
+    ws = np.where(small, w - F(2.5), np.sqrt(np.maximum(w, F(5.0))) - F(3.0)).astype(F)
+    p = np.where(small, _ERFINV_CENTRAL[0], _ERFINV_TAIL[0]).astype(F)
+    for cc, ct in zip(_ERFINV_CENTRAL[1:], _ERFINV_TAIL[1:]):
+        p = (p * ws + np.where(small, cc, ct)).astype(F)
+    return (p * x).astype(F)
+
+
+def truncated_normal(key, lower: float, upper: float, shape) -> np.ndarray:
+    """``jax.random.truncated_normal(key, lower, upper, shape)`` in float32 (jax/_src/random.py ``_truncated_normal``)."""
+    F = np.float32
+    n = int(np.prod(shape))
+    sqrt2 = F(np.sqrt(2.0))
+    a = F(math.erf(float(F(lower) / sqrt2)))
+    b = F(math.erf(float(F(upper) / sqrt2)))
+    bits = _threefry_counts(key, np.arange(n, dtype=_U32))
+    f = ((bits >> _U32(9)) | _U32(0x3F800000)).view(F) - F(1.0)            # [0, 1)
+    u = np.maximum(a, (f * F(b - a) + a).astype(F))
+    out = (sqrt2 * _erf_inv_f32(u)).astype(F)
+    lo = np.nextafter(F(lower), F(np.inf))
+    hi = np.nextafter(F(upper), F(-np.inf))
+    return np.clip(out, lo, hi).reshape(shape)
+
+
+def lecun_normal(key, shape) -> np.ndarray:
+    """``jax.nn.initializers.lecun_normal()`` = variance_scaling(1.0, "fan_in", "truncated_normal"), float32."""
+    std = np.float32(np.sqrt(np.float32(1.0) / np.float32(shape[0]))) / np.float32(_TRUNC_STD)
+    return (truncated_normal(key, -2.0, 2.0, shape) * std).astype(np.float32)
+
+
+def leaf_key(vae_key, name: str) -> np.ndarray:
+    """Key of the leaf ``Encoder/FC0/kernel``: the module key folded with every path component in turn."""
+    key = np.asarray(vae_key, _U32)
+    for part in name.split("/"):
+        key = fold_in_str(key, part)
+    return key
+
+
 def init_params(spec: RunSpec, vae_key: np.ndarray) -> np.ndarray:
-    rng = np.random.default_rng([int(vae_key[0]), int(vae_key[1])])
     parts = []
     for name, shape in layer_shapes(spec):
         n = int(np.prod(shape))
         if name.endswith("kernel"):
-            vals = np.empty(0)
-            while vals.size < n:
-                more = rng.standard_normal(2 * n + 16)
-                vals = np.concatenate([vals, more[np.abs(more) <= 2.0]])
-            parts.append((vals[:n] * (np.sqrt(1.0 / shape[0]) / _TRUNC_STD)).astype(np.float32))
+            parts.append(lecun_normal(leaf_key(vae_key, name), shape).reshape(-1))
         elif name.endswith("bias"):
             parts.append(np.zeros(n, np.float32))
         else:
