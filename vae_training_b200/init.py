@@ -56,17 +56,23 @@ _ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
 
 
 def _threefry2x32(k0, k1, x0, x1):
-    """Threefry-2x32, 20 rounds (jax/_src/prng.py threefry2x32; Random123 known answers in tests/test_host_logic.py)."""
+    """Threefry-2x32, 20 rounds (jax/_src/prng.py threefry2x32; Random123 known answers in tests/test_host_logic.py).
+    Works in place on private copies of the counters (a 16 M-element kernel is drawn without temporaries)."""
     ks = (_U32(k0), _U32(k1), _U32(_U32(k0) ^ _U32(k1) ^ _U32(0x1BD11BDA)))
-    x0 = np.asarray(x0, _U32) + ks[0]
-    x1 = np.asarray(x1, _U32) + ks[1]
+    x0 = np.array(x0, _U32, ndmin=1)
+    x1 = np.array(x1, _U32, ndmin=1)
+    tmp = np.empty_like(x1)
+    x0 += ks[0]
+    x1 += ks[1]
     for i in range(5):
         for r in _ROT[i % 2]:
-            x0 = x0 + x1
-            x1 = (x1 << _U32(r)) | (x1 >> _U32(32 - r))
-            x1 = x1 ^ x0
-        x0 = x0 + ks[(i + 1) % 3]
-        x1 = x1 + ks[(i + 2) % 3] + _U32(i + 1)
+            x0 += x1
+            np.left_shift(x1, _U32(r), out=tmp)
+            x1 >>= _U32(32 - r)
+            x1 |= tmp
+            x1 ^= x0
+        x0 += ks[(i + 1) % 3]
+        x1 += _U32(ks[(i + 2) % 3] + _U32(i + 1))
     return x0, x1
 
 
@@ -78,7 +84,7 @@ def _threefry_counts(key, counts) -> np.ndarray:
         counts = np.concatenate([counts, np.zeros(1, _U32)])
     h = counts.size // 2
     with np.errstate(over="ignore"):
-        y0, y1 = _threefry2x32(key[0], key[1], counts[:h], counts[h:])
+        y0, y1 = _threefry2x32(key[0], key[1], counts[:h], counts[h:])       # (copies the counters)
     return np.concatenate([y0, y1])[:n]
 
 
@@ -99,16 +105,27 @@ _ERFINV_TAIL = [np.float32(c) for c in (-0.000200214257, 0.000100950558, 0.00134
                                         -0.0076224613, 0.00943887047, 1.00167406, 2.83297682)]
 
 
+def _horner_f32(coef, t: np.ndarray) -> np.ndarray:
+    p = np.full_like(t, coef[0])
+    for c in coef[1:]:
+        p *= t
+        p += c
+    return p
+
+
 def _erf_inv_f32(x: np.ndarray) -> np.ndarray:
     F = np.float32
     x = np.asarray(x, F)
-    w = -np.log1p(-(x * x)).astype(F)
-    small = w < F(5.0)
-    ws = np.where(small, w - F(2.5), np.sqrt(np.maximum(w, F(5.0))) - F(3.0)).astype(F)
-    p = np.where(small, _ERFINV_CENTRAL[0], _ERFINV_TAIL[0]).astype(F)
-    for cc, ct in zip(_ERFINV_CENTRAL[1:], _ERFINV_TAIL[1:]):
-        p = (p * ws + np.where(small, cc, ct)).astype(F)
-    return (p * x).astype(F)
+    w = np.multiply(x, x)
+    np.negative(w, out=w)
+    np.log1p(w, out=w)
+    np.negative(w, out=w)                                 # w = -log1p(-x * x)
+    p = _horner_f32(_ERFINV_CENTRAL, w - F(2.5))
+    tail = np.flatnonzero(w.reshape(-1) >= F(5.0))        # |x| > 0.9966: never reached by the [-2, 2] truncation
+    if tail.size:
+        p.reshape(-1)[tail] = _horner_f32(_ERFINV_TAIL, np.sqrt(w.reshape(-1)[tail]) - F(3.0))
+    p *= x
+    return p
 
 
 def truncated_normal(key, lower: float, upper: float, shape) -> np.ndarray:
@@ -141,17 +158,31 @@ def leaf_key(vae_key, name: str) -> np.ndarray:
     return key
 
 
+_INIT_CACHE: dict = {}      # (leaves, vae_key) -> flat parameters; every run of a sweep shares PRNGKey(0) (model.py:29)
+
+
 def init_params(spec: RunSpec, vae_key: np.ndarray) -> np.ndarray:
+    shapes = layer_shapes(spec)
+    ck = (tuple(shapes), int(vae_key[0]), int(vae_key[1]))
+    hit = _INIT_CACHE.get(ck)
+    if hit is not None:
+        return hit.copy()
     parts = []
-    for name, shape in layer_shapes(spec):
-        n = int(np.prod(shape))
-        if name.endswith("kernel"):
-            parts.append(lecun_normal(leaf_key(vae_key, name), shape).reshape(-1))
-        elif name.endswith("bias"):
-            parts.append(np.zeros(n, np.float32))
-        else:
-            parts.append(np.ones(n, np.float32))
-    return np.concatenate(parts)
+    with np.errstate(over="ignore"):
+        for name, shape in shapes:
+            n = int(np.prod(shape))
+            if name.endswith("kernel"):
+                parts.append(lecun_normal(leaf_key(vae_key, name), shape).reshape(-1))
+            elif name.endswith("bias"):
+                parts.append(np.zeros(n, np.float32))
+            else:
+                parts.append(np.ones(n, np.float32))
+    flat = np.concatenate(parts)
+    if flat.size <= (1 << 20):
+        if len(_INIT_CACHE) >= 64:
+            _INIT_CACHE.clear()
+        _INIT_CACHE[ck] = flat.copy()
+    return flat
 
 
 def apply_warm_start(spec: RunSpec, params: np.ndarray, key: torch.Tensor, A: Optional[torch.Tensor],
