@@ -39,6 +39,14 @@ constexpr int kGroupBatch = 100;      // batch size the GM > 1 kernels are compi
 #endif
 // 1: the models of a CTA that share an eps stream (GM > 1) keep ONE copy of it, in the z buffer of the group's
 // lowest-numbered model, instead of storing every normal into each member's buffer (see "Shared eps draw")
+// Launch set-up experiment (-DVAE_SMALL_PREFETCH=1): every global load of the set-up phase (state, Adam step, key chains,
+// the CTA neighbours' model keys) issued right after the job record arrives, BEFORE the shared-memory zero fill, instead
+// of in four to eight dependent round trips between shared-memory stores.  Measured on B200: a launch of ONE model gets
+// 2 us shorter (116.8 -> 114.7 us per 20 steps), but the register allocation of the step loop shifts and the packed
+// kernel loses 3 % in steady state (117.8 -> 114.4 M steps/s at 2000-step launches, 108.1 -> 106.1 M at 20): off.
+#ifndef VAE_SMALL_PREFETCH
+#define VAE_SMALL_PREFETCH 0
+#endif
 #ifndef VAE_SMALL_LEADZ
 #define VAE_SMALL_LEADZ 1
 #endif
@@ -288,24 +296,73 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
 
   // ---- load state
   SMALL_STAMP(1);
+  const int nflat = C::NFLAT + (tunable ? 1 : 0);
+  constexpr int kSkip0 = DR * L, kSkipN = (D - DR) * L;
+  constexpr int kNI = (C::NFLAT + 1 + kT - 1) / kT;                  // state elements per thread
+  constexpr int kNA = (C::AN + kT - 1) / kT, kNS = (kSkipN + kT - 1) / kT;
+  constexpr bool kPrefetch = VAE_SMALL_PREFETCH != 0 && kNI <= 4 && kNA <= 2 && kNS <= 2;
+  float pf_p[kPrefetch ? kNI : 1], pf_m[kPrefetch ? kNI : 1], pf_v[kPrefetch ? kNI : 1], pf_a[kPrefetch && kNA > 0 ? kNA : 1];
+  bool pf_skip = false;
+  int32_t pf_step = 0;
+  uint32_t pf_k0 = 0, pf_k1 = 0, pf_pk0[GM > 1 ? GM : 1], pf_pk1[GM > 1 ? GM : 1];
+  int32_t pf_pb[GM > 1 ? GM : 1], pf_ps[GM > 1 ? GM : 1];
+  if constexpr (kPrefetch) {
+    if constexpr (GM > 1) {                      // the neighbours' records do not wait for this model's own
+      const FusedJobDev* peers = jobs + (int)blockIdx.x * GM;
+#pragma unroll
+      for (int r = 0; r < GM; ++r) {
+        const uint32_t* pk = peers[r].model_key;
+        pf_pb[r] = peers[r].batch; pf_ps[r] = peers[r].shape_id;
+        pf_pk0[r] = pk[0]; pf_pk1[r] = pk[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kNI; ++u) {
+      const int g = t + u * kT;
+      const bool ok = g < nflat && C::padded_of(g, tunable) >= 0;
+      pf_p[u] = ok ? job.params[g] : 0.f; pf_m[u] = ok ? job.adam_m[g] : 0.f; pf_v[u] = ok ? job.adam_v[g] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kNS; ++u) {
+      const int g = t + u * kT;
+      if (g < kSkipN) pf_skip |= job.adam_m[kSkip0 + g] != 0.f || job.adam_v[kSkip0 + g] != 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kNA; ++u) { const int i = t + u * kT; pf_a[u] = i < C::AN ? job.A[i] : 0.f; }
+    pf_step = job.step[0];
+    if (t < 4) { const uint32_t* src = t < 2 ? job.model_key : job.dataset_key; pf_k0 = src[0]; pf_k1 = src[1]; }
+  }
   for (int i = t; i < y.total; i += kT) sm[i] = 0.f;
   __syncthreads();
   SMALL_STAMP(2);
-  const int nflat = C::NFLAT + (tunable ? 1 : 0);
-  for (int g = t; g < nflat; g += kT) {
-    const int o = C::padded_of(g, tunable);
-    if (o >= 0) { P[o] = job.params[g]; M[o] = job.adam_m[g]; V[o] = job.adam_v[g]; }
+  if constexpr (kPrefetch) {
+#pragma unroll
+    for (int u = 0; u < kNI; ++u) {
+      const int g = t + u * kT;
+      const int o = g < nflat ? C::padded_of(g, tunable) : -1;
+      if (o >= 0) { P[o] = pf_p[u]; M[o] = pf_m[u]; V[o] = pf_v[u]; }
+    }
+  } else {
+    for (int g = t; g < nflat; g += kT) {
+      const int o = C::padded_of(g, tunable);
+      if (o >= 0) { P[o] = job.params[g]; M[o] = job.adam_m[g]; V[o] = job.adam_v[g]; }
+    }
   }
   // Encoder kernel rows d >= DR (flat [DR*L, D*L)) multiply exactly-zero padding columns: their gradient
   // is exactly 0 and, with zero Adam moments, flax Adam leaves them unchanged -- they are never loaded.
   // A caller-supplied state with NON-zero moments there (e.g. a checkpoint of a noisy-padding run) still
   // decays: those rows then take the g = 0 Adam update in global memory every step (rare, slow, exact).
-  constexpr int kSkip0 = DR * L, kSkipN = (D - DR) * L;
-  if constexpr (kSkipN > 0) {
-    for (int g = t; g < kSkipN; g += kT)
-      if (job.adam_m[kSkip0 + g] != 0.f || job.adam_v[kSkip0 + g] != 0.f) sm[y.red + 12] = 1.0f;   // benign race: all store 1
+  if constexpr (kPrefetch) {
+    if (pf_skip) sm[y.red + 12] = 1.0f;                                                             // benign race: all store 1
+#pragma unroll
+    for (int u = 0; u < kNA; ++u) { const int i = t + u * kT; if (i < C::AN) sm[y.A + i] = pf_a[u]; }
+  } else {
+    if constexpr (kSkipN > 0) {
+      for (int g = t; g < kSkipN; g += kT)
+        if (job.adam_m[kSkip0 + g] != 0.f || job.adam_v[kSkip0 + g] != 0.f) sm[y.red + 12] = 1.0f;   // benign race: all store 1
+    }
+    for (int i = t; i < C::AN; i += kT) sm[y.A + i] = job.A[i];
   }
-  for (int i = t; i < C::AN; i += kT) sm[y.A + i] = job.A[i];
   for (int b = t; b < B; b += kT) { sm[y.hx + DR * BP + b] = 1.0f; sm[y.hz + L * BP + b] = 1.0f; }   // ones rows
   __syncthreads();
   // Derived per-step constants are double-buffered by step parity: phase B/C of step s
@@ -322,7 +379,7 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   }
   // Adam bias corrections 1/(1 - beta^t): thread kT-1 keeps double running products of the
   // float32 betas and publishes the float32 factors for the NEXT step (slot parity)
-  const int32_t step0 = job.step[0];
+  const int32_t step0 = kPrefetch ? pf_step : job.step[0];
   double b1t = 0.0, b2t = 0.0;
   if (t == kT - 1) {
     b1t = pow((double)job.b1, (double)step0 + 1.0); b2t = pow((double)job.b2, (double)step0 + 1.0);
@@ -331,7 +388,8 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
 
   // ---- key chains: lanes 0,1 own the model-side split, lanes 2,3 the dataset-side one
   uint32_t ck0 = 0, ck1 = 0;           // carried key of this lane's chain
-  if (t < 4) {
+  if constexpr (kPrefetch) { ck0 = pf_k0; ck1 = pf_k1; }
+  else if (t < 4) {
     const uint32_t* src = t < 2 ? job.model_key : job.dataset_key;
     ck0 = src[0]; ck1 = src[1];
   }
@@ -353,7 +411,15 @@ __device__ void fused_small_run(const FusedJobDev* jobs, int64_t n_steps, float*
   const uint32_t self = GM > 1 ? (uint32_t)mi : crank;
   const uint32_t nmemb = GM > 1 ? (uint32_t)GM : csize;
   uint32_t gmask = 1u << self;
-  if (nmemb > 1) {
+  if constexpr (kPrefetch && GM > 1) {
+    uint32_t mk0 = 0u, mk1 = 0u;
+#pragma unroll
+    for (int r = 0; r < GM; ++r) if (r == mi) { mk0 = pf_pk0[r]; mk1 = pf_pk1[r]; }
+    gmask = 0u;
+#pragma unroll
+    for (int r = 0; r < GM; ++r)
+      if (pf_pk0[r] == mk0 && pf_pk1[r] == mk1 && pf_pb[r] == job.batch && pf_ps[r] == job.shape_id) gmask |= 1u << r;
+  } else if (nmemb > 1) {
     const uint32_t mk0 = job.model_key[0], mk1 = job.model_key[1];
     const FusedJobDev* peers = GM > 1 ? jobs + (int)blockIdx.x * GM : jobs + ((int)blockIdx.x - (int)crank);
     gmask = 0u;
